@@ -1,0 +1,225 @@
+/*
+ * zune_jpeg_b200.h -- C ABI of the B200-native pixel-reconstruction path of
+ * etemesi254/zune-jpeg (snapshot 0.2.0).
+ *
+ * The reference has no FFI; its boundary for this path is the crate-private
+ *
+ *   worker::post_process(coeff:&[&[i16];3], component_data:&[Components], idct_func, color_convert_16,
+ *                        input_colorspace, output_colorspace, output:&mut [u8], width)   (src/worker.rs:32-41)
+ *
+ * called once per MCU-row strip from src/mcu.rs:356-368 (baseline) and src/mcu_prog.rs:205-233
+ * (progressive).  A strip is far too small a GPU launch, so this ABI takes WHOLE-IMAGE coefficient planes
+ * (the layout mcu_prog.rs:73-79 allocates, and that the concatenation of mcu.rs's per-strip buffers equals)
+ * and performs every strip's post_process -- dequantise + IDCT + upsample + colour-convert + row de-padding --
+ * for a batch of images in one call.  See INTEGRATION.md for the Rust `extern "C"` block that binds it.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 (ZJ_OK) or a negative
+ * zj_status and never unwinds; the caller owns every buffer; a call is thread-safe per (device, stream).
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns ZJ_ERR_NO_DEVICE.
+ */
+#ifndef ZUNE_JPEG_B200_H
+#define ZUNE_JPEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define ZJ_API __declspec(dllexport)
+#else
+#define ZJ_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------ enums */
+
+/* Ordinals of `ColorSpace` (src/misc.rs:88-106). */
+typedef enum zj_colorspace {
+    ZJ_CS_RGB = 0,
+    ZJ_CS_GRAYSCALE = 1,
+    ZJ_CS_YCBCR = 2,
+    ZJ_CS_CMYK = 3,
+    ZJ_CS_YCCK = 4,
+    ZJ_CS_RGBA = 5,
+    ZJ_CS_RGBX = 6
+} zj_colorspace;
+
+/* Which of the reference's two CPU code paths the output must be bit-identical to.
+ * X86    = ZuneJpegOptions::use_unsafe == true on an AVX2+SSE4.1 host (the default, src/options.rs:31):
+ *          AVX2 IDCT (src/idct/avx2.rs), SSE H upsampler (src/upsampler/sse.rs), scalar V, AVX2 HV
+ *          (src/upsampler/avx2.rs, scalar below 500 samples), AVX2 RGB (src/color_convert/avx.rs).
+ * SCALAR = use_unsafe == false or `--no-default-features`: src/idct/scalar.rs, src/upsampler/scalar.rs,
+ *          src/color_convert/scalar.rs. */
+typedef enum zj_variant { ZJ_VARIANT_X86 = 0, ZJ_VARIANT_SCALAR = 1 } zj_variant;
+
+typedef enum zj_status {
+    ZJ_OK = 0,
+    ZJ_ERR_INVALID_ARG = -1,     /* null pointer, bad enum, inconsistent descriptor                        */
+    ZJ_ERR_UNSUPPORTED = -2,     /* sampling the reference rejects (decoder.rs:512-519, :609-646)          */
+    ZJ_ERR_SHORT_PLANE = -3,     /* a coefficient plane is smaller than the strips it must feed            */
+    ZJ_ERR_SHORT_OUTPUT = -4,    /* out_len[i] < width*height*out_components                               */
+    ZJ_ERR_REF_PANIC = -5,       /* the reference panics on this geometry (tiny widths)     */
+    ZJ_ERR_NO_DEVICE = -6,       /* no CUDA device / bad ordinal -- there is no CPU fallback               */
+    ZJ_ERR_CUDA = -7,            /* a CUDA runtime call failed; zj_gpu_last_cuda_error() has the text      */
+    ZJ_ERR_OOM = -8,             /* device or pinned allocation failed                                     */
+    ZJ_ERR_DECODE = -9           /* host front-end (headers/entropy) error; zj_decoder_error() has details */
+} zj_status;
+
+/* ------------------------------------------------------------ descriptors */
+
+/* One image component as the path sees it: the fields of `Components` (src/components.rs:18-43) that
+ * post_process reads, plus the coefficient plane. */
+typedef struct zj_component {
+    const int16_t *coeff;  /* whole-image plane: blocks in raster order, width_stride/8 blocks per block-row,
+                              64 i16 per block in NATURAL (de-zigzagged, row-major) order -- what
+                              bitstream.rs:343,359 / mcu_prog.rs:298,404-406 produce.  Host or device pointer
+                              depending on the entry point.  May be NULL for components the output colourspace
+                              does not need (worker.rs:59). */
+    uint64_t n_i16;        /* number of i16 in the plane                                                    */
+    int32_t qt[64];        /* quantisation table, natural order (headers.rs:533-543)                        */
+    uint32_t h_samp;       /* Components::horizontal_sample                                                 */
+    uint32_t v_samp;       /* Components::vertical_sample                                                   */
+    uint32_t width_stride; /* Components::width_stride = h_samp * mcu_x * 8 (headers.rs:338)                */
+    uint32_t reserved;
+} zj_component;
+
+#define ZJ_FLAG_PROGRESSIVE 1u /* strips come from mcu_prog.rs:188-233 (zip stops silently) instead of
+                                  mcu.rs:225-369 (chunks.next().unwrap()) -- only matters when the
+                                  over-allocated output runs out of strips, see DESIGN.md                   */
+
+typedef struct zj_image {
+    uint32_t width, height; /* ImageInfo::width/height (decoder.rs:652-668)                                 */
+    uint32_t n_comp;        /* 1 (GRAYSCALE in) or 3 (YCbCr in) = input_colorspace.num_components()         */
+    uint32_t out_cs;        /* zj_colorspace: ZuneJpegOptions::out_colorspace                               */
+    uint32_t variant;       /* zj_variant                                                                   */
+    uint32_t flags;         /* ZJ_FLAG_*                                                                    */
+    zj_component comp[3];   /* comp[0] = Y and carries the maximum sampling factors (decoder.rs:609-646)    */
+} zj_image;
+
+/* ------------------------------------------------------------- GPU path  */
+
+/* Number of CUDA devices visible (0 when there is none; never fails). */
+ZJ_API int zj_gpu_device_count(void);
+
+/* Bytes the reference's decode_buffer returns for this image: width*height*out_components
+ * (mcu.rs:375-379).  Returns 0 on a bad descriptor. */
+ZJ_API size_t zj_output_size(const zj_image *img);
+
+/* Validate a descriptor exactly as the GPU entry points do, without touching a device. */
+ZJ_API int zj_validate_image(const zj_image *img);
+
+/* Replaces every worker::post_process call of `n` images (worker.rs:32-85).
+ * HOST entry point: imgs[i].comp[*].coeff and out[i] are host pointers (pinned memory from
+ * zj_gpu_pinned_alloc makes the copies asynchronous); the call stages H2D, launches, copies D2H and
+ * returns after `stream` has drained.  out[i] receives exactly zj_output_size(&imgs[i]) bytes; bytes the
+ * reference leaves untouched in its zero-initialised Vec (mcu.rs:222) are written as 0. */
+ZJ_API int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
+                              uint8_t *const *out, const size_t *out_len);
+
+/* DEVICE entry point: coefficient planes and outputs already live in the memory of `device`.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream); no host<->device pixel traffic. */
+ZJ_API int zj_gpu_reconstruct_device(int device, void *stream, const zj_image *imgs, size_t n,
+                                     uint8_t *const *out_dev, const size_t *out_len);
+
+/* A reusable plan for a fixed batch of device-resident images: descriptors, strip/tile work lists and qt
+ * tables are uploaded once; zj_batch_run only launches kernels (CUDA-graph friendly). */
+typedef struct zj_batch zj_batch;
+ZJ_API int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *out_dev,
+                           const size_t *out_len, zj_batch **plan);
+ZJ_API int zj_batch_run(zj_batch *plan, void *stream);
+/* kernels launched by one zj_batch_run (for accounting) */
+ZJ_API int zj_batch_launches(const zj_batch *plan);
+/* algorithmic bytes one zj_batch_run moves: coefficient bytes read + output bytes written */
+ZJ_API uint64_t zj_batch_algorithmic_bytes(const zj_batch *plan);
+ZJ_API void zj_batch_destroy(zj_batch *plan);
+
+/* Memory helpers so a non-CUDA host language can stage buffers without linking the CUDA runtime. */
+ZJ_API int zj_gpu_pinned_alloc(size_t bytes, void **p);
+ZJ_API int zj_gpu_pinned_free(void *p);
+ZJ_API int zj_gpu_device_alloc(int device, size_t bytes, void **p);
+ZJ_API int zj_gpu_device_free(int device, void *p);
+ZJ_API int zj_gpu_memcpy_h2d(int device, void *stream, void *dst_dev, const void *src_host, size_t bytes);
+ZJ_API int zj_gpu_memcpy_d2h(int device, void *stream, void *dst_host, const void *src_dev, size_t bytes);
+ZJ_API int zj_gpu_memset(int device, void *stream, void *dst_dev, int value, size_t bytes);
+ZJ_API int zj_gpu_stream_create(int device, void **stream);
+ZJ_API int zj_gpu_stream_destroy(int device, void *stream);
+ZJ_API int zj_gpu_stream_synchronize(int device, void *stream);
+/* CUDA-event timing on `stream` (events see only the stream they are recorded on). */
+ZJ_API int zj_gpu_event_create(int device, void **event);
+ZJ_API int zj_gpu_event_record(int device, void *event, void *stream);
+ZJ_API int zj_gpu_event_elapsed_ms(int device, void *start, void *stop, float *ms);
+ZJ_API int zj_gpu_event_destroy(int device, void *event);
+
+ZJ_API const char *zj_gpu_strerror(int status);
+ZJ_API const char *zj_gpu_last_cuda_error(void);
+/* number of kernel launches this library has issued in this process (monotonic) */
+ZJ_API uint64_t zj_gpu_launch_count(void);
+
+/* ------------------------------------------------- host front-end (C++)  */
+/* The reference's host stage -- headers (src/headers.rs, src/marker.rs, src/decoder.rs:239-411) and entropy
+ * decode (src/bitstream.rs, src/huffman.rs, src/mcu.rs:253-351, src/mcu_prog.rs:49-129,249-430) -- stays on
+ * the CPU.  There is no Rust toolchain in this build environment, so it is restated in C++ here; in a Rust
+ * deployment these symbols are not needed. */
+
+typedef struct zj_options {       /* ZuneJpegOptions (src/options.rs:6-40), same defaults */
+    uint32_t use_unsafe;          /* 1                                                   */
+    uint32_t out_colorspace;      /* ZJ_CS_RGB                                           */
+    uint32_t num_threads;         /* 4                                                   */
+    uint32_t max_width;           /* 16384                                               */
+    uint32_t max_height;          /* 16384                                               */
+    uint32_t max_scans;           /* 64                                                  */
+    uint32_t strict_mode;         /* 0                                                   */
+    int32_t device;               /* CUDA ordinal used by zj_decoder_decode_buffer (0)   */
+} zj_options;
+
+/* DecodeErrors variants (src/errors.rs:16-43) */
+typedef enum zj_decode_error_kind {
+    ZJ_DE_NONE = 0,
+    ZJ_DE_FORMAT = 1,
+    ZJ_DE_FORMAT_STATIC = 2,
+    ZJ_DE_ILLEGAL_MAGIC_BYTES = 3,
+    ZJ_DE_HUFFMAN_DECODE = 4,
+    ZJ_DE_ZERO_ERROR = 5,
+    ZJ_DE_DQT_ERROR = 6,
+    ZJ_DE_SOS_ERROR = 7,
+    ZJ_DE_SOF_ERROR = 8,
+    ZJ_DE_UNSUPPORTED = 9,
+    ZJ_DE_MCU_ERROR = 10,
+    ZJ_DE_EXHAUSTED_DATA = 11,
+    ZJ_DE_LARGE_DIMENSIONS = 12,
+    ZJ_DE_GPU = 13 /* not in the reference: the GPU stage failed, message = zj_gpu_strerror */
+} zj_decode_error_kind;
+
+typedef struct zj_image_info {    /* ImageInfo (src/decoder.rs:652-668) */
+    uint16_t width, height;
+    uint8_t pixel_density;
+    uint8_t sof;                  /* SOFMarkers ordinal (src/misc.rs): 0 BaselineDct, 2 ProgressiveDctHuffman */
+    uint16_t x_density, y_density;
+    uint8_t components;
+    uint8_t valid;                /* 0 until headers were parsed (Decoder::info() -> None, decoder.rs:210)    */
+} zj_image_info;
+
+typedef struct zj_decoder zj_decoder;
+
+ZJ_API void zj_options_default(zj_options *o);
+ZJ_API zj_decoder *zj_decoder_new(const zj_options *o);                /* Decoder::new_with_options           */
+ZJ_API void zj_decoder_free(zj_decoder *d);
+ZJ_API int zj_decoder_read_headers(zj_decoder *d, const uint8_t *buf, size_t len); /* Decoder::read_headers  */
+ZJ_API int zj_decoder_info(const zj_decoder *d, zj_image_info *info);  /* Decoder::info                       */
+ZJ_API uint32_t zj_decoder_out_colorspace(const zj_decoder *d);        /* Decoder::get_output_colorspace      */
+/* Host stage only: headers + entropy decode into coefficient planes owned by the decoder (pinned when a
+ * device is present).  `img` is filled with a descriptor pointing at them (valid until the next call). */
+ZJ_API int zj_decoder_decode_coefficients(zj_decoder *d, const uint8_t *buf, size_t len, zj_image *img);
+/* Decoder::decode_buffer: host stage, then zj_gpu_reconstruct.  *out is malloc'd (zj_buffer_free). */
+ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out,
+                                    size_t *out_len);
+ZJ_API void zj_buffer_free(uint8_t *p);
+ZJ_API int zj_decoder_error_kind(const zj_decoder *d);                 /* zj_decode_error_kind                */
+ZJ_API const char *zj_decoder_error(const zj_decoder *d);              /* Display text of the DecodeErrors    */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZUNE_JPEG_B200_H */
