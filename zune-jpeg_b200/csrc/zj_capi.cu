@@ -1,0 +1,528 @@
+// zj_capi.cu -- the C ABI of include/zune_jpeg_b200.h: descriptor validation, strip/tile planning, device
+// memory plumbing and kernel launches.  No CPU fallback lives here: without a CUDA device every compute
+// entry point returns ZJ_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "../../include/zune_jpeg_b200.h"
+#include "zj_device.h"
+
+namespace zj {
+cudaError_t launch_group(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream);
+}
+
+using namespace zj;
+
+static thread_local char g_cuda_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorMemoryAllocation) return ZJ_ERR_OOM;
+    return ZJ_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+static int num_components(uint32_t cs)  // ColorSpace::num_components, reference src/misc.rs:108-118
+{
+    switch (cs) {
+    case ZJ_CS_RGB: case ZJ_CS_YCBCR: return 3;
+    case ZJ_CS_CMYK: case ZJ_CS_YCCK: case ZJ_CS_RGBA: case ZJ_CS_RGBX: return 4;
+    case ZJ_CS_GRAYSCALE: return 1;
+    default: return 0;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- planning
+struct Plan {
+    int mode, variant, gray, zero_only;
+    uint32_t n_strips, rows, ncomp_used;
+    size_t chunk[3];   // i16 per strip per component
+    size_t out_size;
+    DevImage dev;      // pointers filled by the caller
+    uint32_t grid_tiles;
+};
+
+// Strip geometry of reference src/mcu.rs:139-226 (baseline) / src/mcu_prog.rs:132-203 (progressive) and the
+// colour-writer constants of src/worker.rs:143-251.
+static int plan_image(const zj_image *img, Plan *pl)
+{
+    if (!img) return ZJ_ERR_INVALID_ARG;
+    if (img->n_comp != 1 && img->n_comp != 3) return ZJ_ERR_INVALID_ARG;
+    if (img->width == 0 || img->height == 0 || img->width > 65535 || img->height > 65535) return ZJ_ERR_INVALID_ARG;
+    const int nc = num_components(img->out_cs);
+    if (nc == 0) return ZJ_ERR_INVALID_ARG;
+    if (img->variant != ZJ_VARIANT_X86 && img->variant != ZJ_VARIANT_SCALAR) return ZJ_ERR_INVALID_ARG;
+    const uint32_t h = img->comp[0].h_samp, v = img->comp[0].v_samp;
+    if (img->n_comp == 1 && (h != 1 || v != 1)) return ZJ_ERR_UNSUPPORTED;  // mcu.rs:171-196 resets these before the path
+    for (uint32_t z = 1; z < img->n_comp; z++)
+        if (img->comp[z].h_samp != 1 || img->comp[z].v_samp != 1) return ZJ_ERR_UNSUPPORTED;  // decoder.rs:634-643
+    int mode;
+    if (h == 1 && v == 1) mode = MODE_NONE;
+    else if (h == 2 && v == 1) mode = MODE_H;
+    else if (h == 1 && v == 2) mode = MODE_V;
+    else if (h == 2 && v == 2) mode = MODE_HV;
+    else return ZJ_ERR_UNSUPPORTED;  // decoder.rs:512-519
+
+    const uint32_t w = img->width, hh = img->height;
+    const uint32_t mcu_x = (w + 8 * h - 1) / (8 * h), mcu_y = (hh + 8 * v - 1) / (8 * v);  // headers.rs:316-318
+    for (uint32_t z = 0; z < img->n_comp; z++) {
+        if (img->comp[z].width_stride != img->comp[z].h_samp * mcu_x * 8) return ZJ_ERR_INVALID_ARG;  // headers.rs:338
+        for (int k = 0; k < 64; k++)
+            if (img->comp[z].qt[k] < 0 || img->comp[z].qt[k] > 255) return ZJ_ERR_INVALID_ARG;  // 8-bit tables only, headers.rs:156-173
+    }
+    memset(pl, 0, sizeof(*pl));
+    pl->mode = mode;
+    pl->variant = (int)img->variant;
+    uint32_t n_strips, ybr, cbr;
+    switch (mode) {
+    case MODE_H: n_strips = mcu_y / 2; ybr = 2; cbr = 2; break;   // mcu.rs:147-154 -- Q1: odd MCU row dropped
+    case MODE_HV: n_strips = mcu_y / 2; ybr = 4; cbr = 2; break;  // mcu.rs:155-159
+    case MODE_V: n_strips = mcu_y; ybr = 2; cbr = 1; break;       // mcu.rs:160-163
+    default: n_strips = (hh + 7) / 8; ybr = 1; cbr = 1; break;    // mcu.rs:164-169
+    }
+    const uint32_t rows = 8 * h * v;
+    const size_t out_chunk = (size_t)w * nc * rows;               // mcu.rs:226
+    const size_t capacity = (size_t)(uint16_t)(w + 8) * (size_t)(uint16_t)(hh + 8);  // mcu.rs:198 (u16 add)
+    const size_t extra = (mode != MODE_NONE ? 128u : 0u) * (size_t)hh * nc;           // mcu.rs:207
+    const size_t avail = (capacity * nc + extra) / out_chunk;
+    if (n_strips > avail) {
+        if (img->flags & ZJ_FLAG_PROGRESSIVE) n_strips = (uint32_t)avail;  // mcu_prog.rs:206-209, zip stops
+        else return ZJ_ERR_REF_PANIC;                                      // mcu.rs:354, chunks.next().unwrap()
+    }
+    pl->n_strips = n_strips;
+    pl->rows = rows;
+    pl->out_size = (size_t)w * hh * nc;
+    pl->chunk[0] = (size_t)ybr * h * mcu_x * 64;
+    pl->chunk[1] = pl->chunk[2] = (size_t)cbr * mcu_x * 64;
+
+    const uint32_t in_cs = img->n_comp == 1 ? ZJ_CS_GRAYSCALE : ZJ_CS_YCBCR;
+    const uint32_t oc = img->out_cs;
+    uint32_t kind;
+    if (oc == ZJ_CS_GRAYSCALE) kind = OUT_GRAY;                                       // worker.rs:115-118
+    else if (in_cs == ZJ_CS_YCBCR && oc == ZJ_CS_YCBCR) kind = OUT_YCC;               // worker.rs:120-123
+    else if (in_cs == ZJ_CS_YCBCR && (oc == ZJ_CS_RGB || oc == ZJ_CS_RGBA || oc == ZJ_CS_RGBX)) kind = OUT_RGB;  // :125-129
+    else kind = OUT_ZERO;                                                             // worker.rs:131-132
+    pl->gray = kind == OUT_GRAY;
+    pl->zero_only = kind == OUT_ZERO;
+    pl->ncomp_used = kind == OUT_GRAY ? 1u : (kind == OUT_ZERO ? 0u : 3u);  // min(in, out) comps are IDCT'd; unused results are dropped
+
+    DevImage &d = pl->dev;
+    d.width = w; d.height = hh; d.nc = (uint32_t)nc; d.out_kind = kind;
+    d.mcu_x = mcu_x; d.n_strips = n_strips;
+    d.Wp = img->comp[0].width_stride;
+    d.W = img->n_comp == 3 ? img->comp[1].width_stride : 0;
+    d.stride = w * (uint32_t)nc;
+    d.T = 0xffffffffu;
+    d.small_width = 0;
+    d.hv_avx = (mode == MODE_HV && img->variant == ZJ_VARIANT_X86 && (size_t)16 * d.W >= 500) ? 1u : 0u;  // upsampler/avx2.rs:16
+    for (uint32_t z = 0; z < img->n_comp; z++)
+        for (int k = 0; k < 32; k++)
+            d.qtw[z][k] = (uint32_t)img->comp[z].qt[2 * k] | ((uint32_t)img->comp[z].qt[2 * k + 1] << 24);
+
+    if (kind == OUT_GRAY) {
+        // ycbcr_to_grayscale (color_convert/scalar.rs:97-112): width_mcu = len / width must equal the strip's row
+        // count, otherwise the chunking overruns the strip's output slice and the reference panics (Q7).
+        const size_t len = (size_t)rows * d.Wp;
+        if (len / w != rows) return ZJ_ERR_REF_PANIC;
+        d.gray_rows_ok = 1;
+        d.n_tiles = (d.Wp / 8 + ZJ_THREADS - 1) / ZJ_THREADS;
+        pl->grid_tiles = d.n_tiles;
+    } else if (kind == OUT_YCC) {
+        d.n_norm = w; d.P = 3 * w;
+    } else if (kind == OUT_RGB) {
+        if (w < 16) {
+            if (d.Wp > 16) return ZJ_ERR_REF_PANIC;  // copy_from_slice into [0;16], worker.rs:183
+            d.small_width = 1;
+        } else {
+            const uint32_t E = d.Wp / 16 > 0 ? d.Wp / 16 - 1 : 0;  // worker.rs:171
+            d.n_norm = 16 * E;
+            d.P = 48 * E;
+            if (d.P > d.stride) return ZJ_ERR_REF_PANIC;
+            const uint32_t room = d.stride - d.P;
+            const uint32_t diff = room < 64 ? 64 - room : 0;       // worker.rs:221
+            d.T = d.P > diff ? d.P - diff : 0;                     // worker.rs:223
+            if (d.T + 48 > d.stride) return ZJ_ERR_REF_PANIC;
+        }
+    }
+    if (kind != OUT_GRAY) {
+        const int tmv[4] = {TM_NONE, TM_H, TM_V, TM_HV};
+        d.n_tiles = (mcu_x + tmv[mode] - 1) / tmv[mode];
+        pl->grid_tiles = d.n_tiles;
+    }
+    return ZJ_OK;
+}
+
+static int check_buffers(const zj_image *img, const Plan &pl, const void *out, size_t out_len)
+{
+    for (uint32_t z = 0; z < pl.ncomp_used; z++) {
+        if (!img->comp[z].coeff) return ZJ_ERR_INVALID_ARG;
+        if (img->comp[z].n_i16 < (uint64_t)pl.n_strips * pl.chunk[z]) return ZJ_ERR_SHORT_PLANE;
+    }
+    if (!out) return ZJ_ERR_INVALID_ARG;
+    if (out_len < pl.out_size) return ZJ_ERR_SHORT_OUTPUT;
+    return ZJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batches
+struct zj_batch {
+    int device;
+    std::vector<LaunchGroup> groups;
+    std::vector<std::pair<uint8_t *, size_t>> zero_only;  // outputs that are just memset (worker.rs:131-132)
+    DevImage *d_images;
+    size_t n_images;
+    uint64_t algo_bytes;
+};
+
+static int set_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return ZJ_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return ZJ_ERR_NO_DEVICE;
+    CU(cudaSetDevice(device));
+    return ZJ_OK;
+}
+
+extern "C" {
+
+int zj_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+size_t zj_output_size(const zj_image *img)
+{
+    Plan pl;
+    int rc = plan_image(img, &pl);
+    if (rc != ZJ_OK && rc != ZJ_ERR_REF_PANIC) return 0;
+    return img ? (size_t)img->width * img->height * num_components(img->out_cs) : 0;
+}
+
+int zj_validate_image(const zj_image *img)
+{
+    Plan pl;
+    int rc = plan_image(img, &pl);
+    if (rc != ZJ_OK) return rc;
+    for (uint32_t z = 0; z < pl.ncomp_used; z++)
+        if (img->comp[z].n_i16 < (uint64_t)pl.n_strips * pl.chunk[z]) return ZJ_ERR_SHORT_PLANE;
+    return ZJ_OK;
+}
+
+int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *out_dev, const size_t *out_len, zj_batch **plan)
+{
+    if (!plan) return ZJ_ERR_INVALID_ARG;
+    *plan = nullptr;
+    if ((!imgs || !out_dev || !out_len) && n) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(device);
+    if (rc) return rc;
+    std::vector<Plan> plans(n);
+    for (size_t i = 0; i < n; i++) {
+        rc = plan_image(&imgs[i], &plans[i]);
+        if (rc) return rc;
+        rc = check_buffers(&imgs[i], plans[i], out_dev[i], out_len[i]);
+        if (rc) return rc;
+        for (int z = 0; z < 3; z++) plans[i].dev.coeff[z] = (uint32_t)z < plans[i].ncomp_used ? imgs[i].comp[z].coeff : nullptr;
+        plans[i].dev.out = out_dev[i];
+    }
+    zj_batch *b = new zj_batch();
+    b->device = device;
+    b->d_images = nullptr;
+    b->n_images = 0;
+    b->algo_bytes = 0;
+    // group by kernel: (gray, mode, variant); stable so images keep their relative order
+    std::vector<size_t> order;
+    for (size_t i = 0; i < n; i++) {
+        if (plans[i].zero_only) b->zero_only.push_back({out_dev[i], plans[i].out_size});
+        else order.push_back(i);
+        b->algo_bytes += plans[i].out_size;
+        for (uint32_t z = 0; z < plans[i].ncomp_used; z++) b->algo_bytes += (uint64_t)plans[i].n_strips * plans[i].chunk[z] * 2;
+    }
+    auto key = [&](size_t i) { return plans[i].gray * 16 + plans[i].mode * 2 + plans[i].variant; };
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t c) { return key(a) < key(c); });
+    std::vector<DevImage> host(order.size());
+    for (size_t k = 0; k < order.size(); k++) host[k] = plans[order[k]].dev;
+    for (size_t k = 0; k < order.size();) {
+        size_t e = k;
+        LaunchGroup g{};
+        g.gray = plans[order[k]].gray; g.mode = plans[order[k]].mode; g.variant = plans[order[k]].variant;
+        g.first = (uint32_t)k;
+        while (e < order.size() && key(order[e]) == key(order[k]) && e - k < 65535) {
+            g.max_tiles = std::max(g.max_tiles, plans[order[e]].grid_tiles);
+            g.max_strips = std::max(g.max_strips, plans[order[e]].n_strips);
+            e++;
+        }
+        g.count = (uint32_t)(e - k);
+        b->groups.push_back(g);
+        k = e;
+    }
+    if (!host.empty()) {
+        cudaError_t e = cudaMalloc(&b->d_images, host.size() * sizeof(DevImage));
+        if (e != cudaSuccess) { delete b; return cuda_fail(e, "cudaMalloc(descriptors)"); }
+        e = cudaMemcpy(b->d_images, host.data(), host.size() * sizeof(DevImage), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(b->d_images); delete b; return cuda_fail(e, "cudaMemcpy(descriptors)"); }
+        b->n_images = host.size();
+    }
+    *plan = b;
+    return ZJ_OK;
+}
+
+int zj_batch_run(zj_batch *b, void *stream)
+{
+    if (!b) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(b->device);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (auto &z : b->zero_only) CU(cudaMemsetAsync(z.first, 0, z.second, s));
+    for (auto &g : b->groups) {
+        CU(launch_group(b->d_images, g, s));
+        g_launches.fetch_add(1);
+    }
+    return ZJ_OK;
+}
+
+int zj_batch_launches(const zj_batch *b) { return b ? (int)b->groups.size() : 0; }
+uint64_t zj_batch_algorithmic_bytes(const zj_batch *b) { return b ? b->algo_bytes : 0; }
+
+void zj_batch_destroy(zj_batch *b)
+{
+    if (!b) return;
+    if (b->d_images) { cudaSetDevice(b->device); cudaFree(b->d_images); }
+    delete b;
+}
+
+int zj_gpu_reconstruct_device(int device, void *stream, const zj_image *imgs, size_t n, uint8_t *const *out_dev, const size_t *out_len)
+{
+    zj_batch *b = nullptr;
+    int rc = zj_batch_create(device, imgs, n, out_dev, out_len, &b);
+    if (rc) return rc;
+    rc = zj_batch_run(b, stream);
+    // the descriptor array must outlive the kernels
+    if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize"); }
+    zj_batch_destroy(b);
+    return rc;
+}
+
+// Host entry point: stage planes H2D, run, copy pixels D2H.  Images are processed in sub-batches on two
+// internal streams so that the copies of one sub-batch overlap the kernels of the other.
+int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n, uint8_t *const *out, const size_t *out_len)
+{
+    if ((!imgs || !out || !out_len) && n) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(device);
+    if (rc) return rc;
+    std::vector<Plan> plans(n);
+    for (size_t i = 0; i < n; i++) {
+        rc = plan_image(&imgs[i], &plans[i]);
+        if (rc) return rc;
+        rc = check_buffers(&imgs[i], plans[i], out[i], out_len[i]);
+        if (rc) return rc;
+    }
+    cudaStream_t user = (cudaStream_t)stream;
+    constexpr int NS = 2;
+    cudaStream_t st[NS];
+    for (int k = 0; k < NS; k++) CU(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+    // everything issued on `user` before this call must be visible
+    cudaEvent_t ev_in;
+    CU(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev_in, user));
+    for (int k = 0; k < NS; k++) CU(cudaStreamWaitEvent(st[k], ev_in, 0));
+
+    const size_t budget = (size_t)1 << 30;  // ~1 GiB of device staging per sub-batch
+    std::vector<void *> to_free;
+    std::vector<zj_batch *> batches;
+    size_t i = 0;
+    int which = 0;
+    rc = ZJ_OK;
+    while (i < n && rc == ZJ_OK) {
+        size_t j = i, bytes = 0;
+        while (j < n) {
+            size_t need = plans[j].out_size;
+            for (uint32_t z = 0; z < plans[j].ncomp_used; z++) need += (size_t)plans[j].n_strips * plans[j].chunk[z] * 2;
+            if (j > i && bytes + need > budget) break;
+            bytes += need + 4 * 256;
+            j++;
+        }
+        cudaStream_t s = st[which];
+        which = (which + 1) % NS;
+        uint8_t *pool = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&pool, bytes, s);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocAsync"); break; }
+        to_free.push_back(pool);
+        std::vector<zj_image> dimgs(imgs + i, imgs + j);
+        std::vector<uint8_t *> douts(j - i);
+        std::vector<size_t> dlens(j - i);
+        size_t off = 0;
+        auto take = [&](size_t nbytes) { uint8_t *p = pool + off; off += (nbytes + 255) & ~(size_t)255; return p; };
+        for (size_t k = i; k < j && rc == ZJ_OK; k++) {
+            for (uint32_t z = 0; z < plans[k].ncomp_used; z++) {
+                const size_t nb = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
+                uint8_t *p = take(nb);
+                e = cudaMemcpyAsync(p, imgs[k].comp[z].coeff, nb, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+                dimgs[k - i].comp[z].coeff = (const int16_t *)p;
+            }
+            douts[k - i] = take(plans[k].out_size);
+            dlens[k - i] = plans[k].out_size;
+        }
+        if (rc != ZJ_OK) break;
+        zj_batch *b = nullptr;
+        rc = zj_batch_create(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b);
+        if (rc != ZJ_OK) break;
+        batches.push_back(b);
+        rc = zj_batch_run(b, s);
+        if (rc != ZJ_OK) break;
+        for (size_t k = i; k < j; k++) {
+            e = cudaMemcpyAsync(out[k], douts[k - i], plans[k].out_size, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
+        }
+        cudaFreeAsync(pool, s);
+        to_free.pop_back();
+        i = j;
+    }
+    for (int k = 0; k < NS; k++) {
+        cudaError_t e = cudaStreamSynchronize(st[k]);
+        if (e != cudaSuccess && rc == ZJ_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    for (void *p : to_free) cudaFree(p);
+    for (zj_batch *b : batches) zj_batch_destroy(b);
+    for (int k = 0; k < NS; k++) cudaStreamDestroy(st[k]);
+    cudaEventDestroy(ev_in);
+    if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize(user); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(user)"); }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- memory helpers
+int zj_gpu_pinned_alloc(size_t bytes, void **p)
+{
+    if (!p) return ZJ_ERR_INVALID_ARG;
+    *p = nullptr;
+    if (zj_gpu_device_count() == 0) return ZJ_ERR_NO_DEVICE;
+    CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+    return ZJ_OK;
+}
+int zj_gpu_pinned_free(void *p) { if (p) CU(cudaFreeHost(p)); return ZJ_OK; }
+int zj_gpu_device_alloc(int device, size_t bytes, void **p)
+{
+    if (!p) return ZJ_ERR_INVALID_ARG;
+    *p = nullptr;
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaMalloc(p, bytes ? bytes : 1));
+    return ZJ_OK;
+}
+int zj_gpu_device_free(int device, void *p)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    if (p) CU(cudaFree(p));
+    return ZJ_OK;
+}
+int zj_gpu_memcpy_h2d(int device, void *stream, void *dst, const void *src, size_t bytes)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return ZJ_OK;
+}
+int zj_gpu_memcpy_d2h(int device, void *stream, void *dst, const void *src, size_t bytes)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return ZJ_OK;
+}
+int zj_gpu_memset(int device, void *stream, void *dst, int value, size_t bytes)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return ZJ_OK;
+}
+int zj_gpu_stream_create(int device, void **stream)
+{
+    if (!stream) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(device);
+    if (rc) return rc;
+    cudaStream_t s;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return ZJ_OK;
+}
+int zj_gpu_stream_destroy(int device, void *stream)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaStreamDestroy((cudaStream_t)stream));
+    return ZJ_OK;
+}
+int zj_gpu_stream_synchronize(int device, void *stream)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return ZJ_OK;
+}
+int zj_gpu_event_create(int device, void **event)
+{
+    if (!event) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(device);
+    if (rc) return rc;
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    *event = (void *)e;
+    return ZJ_OK;
+}
+int zj_gpu_event_record(int device, void *event, void *stream)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return ZJ_OK;
+}
+int zj_gpu_event_elapsed_ms(int device, void *start, void *stop, float *ms)
+{
+    if (!ms) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaEventSynchronize((cudaEvent_t)stop));
+    CU(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return ZJ_OK;
+}
+int zj_gpu_event_destroy(int device, void *event)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(cudaEventDestroy((cudaEvent_t)event));
+    return ZJ_OK;
+}
+
+const char *zj_gpu_strerror(int status)
+{
+    switch (status) {
+    case ZJ_OK: return "ok";
+    case ZJ_ERR_INVALID_ARG: return "invalid argument or inconsistent image descriptor";
+    case ZJ_ERR_UNSUPPORTED: return "Unknown down-sampling method, cannot continue";  // decoder.rs:512-519
+    case ZJ_ERR_SHORT_PLANE: return "coefficient plane smaller than the strips it must feed";
+    case ZJ_ERR_SHORT_OUTPUT: return "output buffer smaller than width*height*components";
+    case ZJ_ERR_REF_PANIC: return "the reference decoder panics on this geometry";
+    case ZJ_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case ZJ_ERR_CUDA: return "CUDA runtime error (see zj_gpu_last_cuda_error)";
+    case ZJ_ERR_OOM: return "out of device or pinned memory";
+    case ZJ_ERR_DECODE: return "JPEG header / entropy decode error (see zj_decoder_error)";
+    default: return "unknown status";
+    }
+}
+const char *zj_gpu_last_cuda_error(void) { return g_cuda_err; }
+uint64_t zj_gpu_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// zj_device.h -- descriptors shared by the host-side planner (zj_capi.cu) and the kernels (zj_kernels.cu).
+//
+// Vocabulary follows the reference: an image is cut into MCU-row *strips* (the unit of
+// worker::post_process, reference src/worker.rs:32; geometry src/mcu.rs:139-226, src/mcu_prog.rs:132-203);
+// a strip is cut into *tiles* of TM MCU columns, one CTA per tile.
+#pragma once
+#include <stdint.h>
+
+namespace zj {
+
+enum Mode : int { MODE_NONE = 0, MODE_H = 1, MODE_V = 2, MODE_HV = 3 };  // SubSampRatios, components.rs:130
+enum OutKind : int {
+    OUT_RGB = 0,   // YCbCr -> RGB | "RGBA" | "RGBX": the 3-byte conv16 + row-tail rule (worker.rs:143-251)
+    OUT_YCC = 1,   // YCbCr -> YCbCr interleave (color_convert/scalar.rs:119-169)
+    OUT_GRAY = 2,  // (YCbCr | GRAYSCALE) -> GRAYSCALE (color_convert/scalar.rs:91-114)
+    OUT_ZERO = 3   // every other pair: nothing is written (worker.rs:131-132)
+};
+
+// MCU columns per tile, chosen so that one CTA of ZJ_THREADS threads has about one 8x8 block per thread
+// (including the chroma halo blocks):                 blocks / MCU column        + halo
+//   NONE: 3 blocks  -> TM 40 -> 120                   H: 8 -> TM 15 -> 120 + 8
+//   V:    4 blocks  -> TM 32 -> 128                   HV: 12 -> TM 10 -> 120 + 8 (+4 in tile 0)
+constexpr int ZJ_THREADS = 128;
+constexpr int TM_NONE = 40, TM_H = 15, TM_V = 32, TM_HV = 10, TM_GRAY = 128;
+
+struct DevImage {
+    const int16_t *coeff[3];  // device pointers, whole-image planes
+    uint8_t *out;             // device pointer, width*height*nc bytes
+    uint32_t qtw[3][32];      // quantisation tables packed for dp2a: word k = q[2k] | q[2k+1] << 24
+    uint32_t width, height;
+    uint32_t nc;              // output bytes per pixel
+    uint32_t out_kind;        // OutKind
+    uint32_t mcu_x;           // MCU columns (headers.rs:316)
+    uint32_t n_strips;        // strips the reference processes (Q1: may not cover the image)
+    uint32_t n_tiles;         // tiles per strip
+    uint32_t Wp;              // luma plane row width = comp[0].width_stride
+    uint32_t W;               // chroma plane row width = comp[1].width_stride (0 if no chroma)
+    uint32_t stride;          // output row stride in bytes = width*nc
+    // colour writer constants (worker.rs:171,221-223)
+    uint32_t n_norm;          // samples [0, n_norm) of a row are written at byte 3*s ("normal" chunks)
+    uint32_t P;               // 3*n_norm for RGB; bytes >= P not covered by the tail stay zero
+    uint32_t T;               // tail chunk (samples Wp-16..Wp-1) lands at bytes [T, T+48); 0xffffffff = none
+    uint32_t small_width;     // width < 16: temp-buffer path (worker.rs:158-163,176-198)
+    uint32_t hv_avx;          // HV + X86 + chroma strip >= 500 samples -> AVX2 closed form
+    uint32_t gray_rows_ok;    // Q7 resolved: 1 = plain row copy is what the reference does
+};
+
+// Host-side launch plan entry: one kernel launch per (mode, variant, out-kind class) group.
+struct LaunchGroup {
+    int mode, variant, gray;  // gray = luma-only kernel
+    uint32_t first, count;    // images [first, first+count) of the sorted device array
+    uint32_t max_tiles, max_strips;
+};
+
+}  // namespace zj

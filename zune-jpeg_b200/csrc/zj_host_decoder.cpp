@@ -1,0 +1,1195 @@
+// zj_host_decoder.cpp -- the HOST stage in front of the GPU path: JPEG headers and Huffman entropy decode
+// into whole-image i16 coefficient planes, plus the `Decoder` object of the reference's public API.
+//
+// In a Rust deployment this stage is the reference's own code (src/headers.rs, src/marker.rs, src/huffman.rs,
+// src/bitstream.rs, src/mcu.rs, src/mcu_prog.rs) and only the GPU entry points are bound.
+// There is no Rust toolchain in this build environment, so the stage is restated here in C++ with the same
+// observable behaviour: same marker loop, same table construction, same bit-reader state machine (including
+// what happens after a marker is met inside a scan), same restart bookkeeping, same errors.
+// The branchy bit-serial work stays on the CPU by design; everything after it runs in zj_kernels.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/zune_jpeg_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ errors
+struct DecodeError {  // DecodeErrors, reference src/errors.rs:16-43
+    int kind;
+    std::string msg;
+};
+#define FAIL(k, m) throw DecodeError{(k), (m)}
+
+static std::string fmt(const char *f, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof(buf), f, ap);
+    va_end(ap);
+    return std::string(buf);
+}
+static const char *IO_EOF = "Error decoding an image:\n failed to fill whole buffer";  // From<io::Error>, errors.rs:120-126
+
+// ------------------------------------------------------------------------------------------------ markers
+enum MarkerKind { M_SOF, M_DHT, M_DAC, M_RST, M_SOI, M_EOI, M_SOS, M_DQT, M_DNL, M_DRI, M_APP, M_COM };
+struct Marker { int kind; int n; bool operator==(const Marker &o) const { return kind == o.kind && n == o.n; } };
+
+static bool marker_from_u8(uint8_t b, Marker *m)  // Marker::from_u8, src/marker.rs:48-78
+{
+    switch (b) {
+    case 0xFE: *m = {M_COM, 0}; return true;
+    case 0xC0: *m = {M_SOF, 0}; return true;
+    case 0xC2: *m = {M_SOF, 2}; return true;
+    case 0xC4: *m = {M_DHT, 0}; return true;
+    case 0xCC: *m = {M_DAC, 0}; return true;
+    case 0xD8: *m = {M_SOI, 0}; return true;
+    case 0xD9: *m = {M_EOI, 0}; return true;
+    case 0xDA: *m = {M_SOS, 0}; return true;
+    case 0xDB: *m = {M_DQT, 0}; return true;
+    case 0xDC: *m = {M_DNL, 0}; return true;
+    case 0xDD: *m = {M_DRI, 0}; return true;
+    case 0xE0: *m = {M_APP, 0}; return true;
+    case 0xE1: *m = {M_APP, 1}; return true;
+    case 0xEE: *m = {M_APP, 14}; return true;
+    default:
+        if (b >= 0xD0 && b <= 0xD7) { *m = {M_RST, b - 0xD0}; return true; }
+        return false;
+    }
+}
+static std::string marker_debug(const Marker &m)  // #[derive(Debug)]
+{
+    switch (m.kind) {
+    case M_SOF: return fmt("SOF(%d)", m.n);
+    case M_DHT: return "DHT";
+    case M_DAC: return "DAC";
+    case M_RST: return fmt("RST(%d)", m.n);
+    case M_SOI: return "SOI";
+    case M_EOI: return "EOI";
+    case M_SOS: return "SOS";
+    case M_DQT: return "DQT";
+    case M_DNL: return "DNL";
+    case M_DRI: return "DRI";
+    case M_APP: return fmt("APP(%d)", m.n);
+    default: return "COM";
+    }
+}
+
+static const uint8_t UN_ZIGZAG[80] = {  // src/misc.rs:30-41 (16 entries of padding)
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
+    63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+// ------------------------------------------------------------------------------------------------ cursor
+struct Cursor {  // std::io::Cursor<Vec<u8>> as the reference uses it
+    const uint8_t *data;
+    size_t len;
+    size_t pos;
+    uint8_t read_byte()  // misc::read_byte, src/misc.rs:268-278
+    {
+        if (pos >= len) FAIL(ZJ_DE_FORMAT, IO_EOF);
+        return data[pos++];
+    }
+    uint16_t read_u16_be()  // misc::read_u16_be, src/misc.rs:281-296: a short read is ExhaustedData
+    {
+        size_t avail = pos < len ? len - pos : 0;
+        if (avail < 2) { pos += avail; FAIL(ZJ_DE_EXHAUSTED_DATA, ""); }
+        uint16_t v = (uint16_t)((data[pos] << 8) | data[pos + 1]);
+        pos += 2;
+        return v;
+    }
+    void read_exact(uint8_t *dst, size_t n, int kind, const std::string &msg)
+    {
+        size_t avail = pos < len ? len - pos : 0;
+        if (avail < n) { pos = len; FAIL(kind, msg); }
+        memcpy(dst, data + pos, n);
+        pos += n;
+    }
+    void consume(size_t n) { pos += n; }
+    uint64_t read_u8_or_zero()  // bitstream.rs:696-703
+    {
+        uint64_t v = pos < len ? data[pos] : 0;
+        pos++;
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ Huffman
+constexpr int HUFF_LOOKAHEAD = 9;  // src/huffman.rs:9
+
+struct HuffmanTable {  // src/huffman.rs:14-41
+    int32_t maxcode[18];
+    int32_t offset[18];
+    int32_t lookup[1 << HUFF_LOOKAHEAD];
+    int16_t ac_lookup[1 << HUFF_LOOKAHEAD];
+    bool has_ac_lookup;
+    uint8_t bits[17];
+    uint8_t values[256];
+    bool present;
+};
+
+// HuffmanTable::new + make_derived_table, src/huffman.rs:45-276
+static void build_huffman(HuffmanTable &p, const uint8_t codes[17], const uint8_t values[256], bool is_dc, bool is_progressive)
+{
+    const int32_t too_long = (HUFF_LOOKAHEAD + 1) << HUFF_LOOKAHEAD;
+    memset(p.maxcode, 0, sizeof(p.maxcode));
+    memset(p.offset, 0, sizeof(p.offset));
+    for (int i = 0; i < (1 << HUFF_LOOKAHEAD); i++) p.lookup[i] = too_long;
+    memcpy(p.bits, codes, 17);
+    memcpy(p.values, values, 256);
+    p.has_ac_lookup = false;
+    p.present = true;
+
+    uint8_t huff_size[257] = {0};
+    uint32_t huff_code[257] = {0};
+    size_t k = 0;
+    for (int l = 1; l <= 16; l++)
+        for (int i = p.bits[l]; i != 0; i--) huff_size[k++] = (uint8_t)l;  // figure C.1
+    huff_size[k] = 0;
+    const size_t num_symbols = k;
+    uint32_t code = 0;
+    int32_t si = huff_size[0];
+    k = 0;
+    while (huff_size[k] != 0) {  // figure C.2
+        while ((int32_t)huff_size[k] == si) { huff_code[k] = code; code++; k++; }
+        p.maxcode[si] = (int32_t)(code << (16 - si));
+        if ((int32_t)code >= (1 << si)) FAIL(ZJ_DE_HUFFMAN_DECODE, "Bad Huffman Table");
+        code <<= 1;
+        si++;
+    }
+    k = 0;
+    for (int l = 0; l <= 16; l++) {  // figure F.15
+        if (p.bits[l] == 0) p.maxcode[l] = -1;
+        else { p.offset[l] = (int32_t)k - (int32_t)huff_code[k]; k += p.bits[l]; }
+    }
+    p.offset[17] = 0;
+    p.maxcode[17] = 0x000FFFFF;
+    k = 0;
+    for (int l = 1; l <= HUFF_LOOKAHEAD; l++) {
+        for (int i = 1; i <= (int)p.bits[l]; i++) {
+            size_t look_bits = (size_t)huff_code[k] << (HUFF_LOOKAHEAD - l);
+            for (int c = 0; c < (1 << (HUFF_LOOKAHEAD - l)); c++) { p.lookup[look_bits] = (l << HUFF_LOOKAHEAD) | p.values[k]; look_bits++; }
+            k++;
+        }
+    }
+    if (!is_dc) {  // fast AC table: decode + receive_extend in one lookup (huffman.rs:180-257)
+        int16_t fast[1 << HUFF_LOOKAHEAD];
+        for (int i = 0; i < (1 << HUFF_LOOKAHEAD); i++) fast[i] = 255;
+        for (size_t i = 0; i < num_symbols; i++) {
+            const int s = huff_size[i];
+            if (s <= HUFF_LOOKAHEAD) {
+                const size_t c = (size_t)(huff_code[i] << (HUFF_LOOKAHEAD - s)), m = (size_t)1 << (HUFF_LOOKAHEAD - s);
+                for (size_t j = 0; j < m; j++) fast[c + j] = (int16_t)i;
+            }
+        }
+        for (int i = 0; i < (1 << HUFF_LOOKAHEAD); i++) {
+            p.ac_lookup[i] = 0;
+            const int16_t fast_v = fast[i];
+            if (fast_v < 255) {
+                const uint8_t rs = p.values[fast_v];
+                const int16_t run = (rs >> 4) & 15, mag_bits = rs & 15, len = huff_size[fast_v];
+                if (mag_bits == 0 && !is_progressive) {
+                    const int16_t new_run = run == 0 ? 63 : run;
+                    p.ac_lookup[i] = (int16_t)((new_run << 4) + len);
+                } else if (mag_bits != 0 && (len + mag_bits) <= HUFF_LOOKAHEAD) {
+                    int16_t kk = (int16_t)((((int16_t)i << len) & ((1 << HUFF_LOOKAHEAD) - 1)) >> (HUFF_LOOKAHEAD - mag_bits));
+                    const int16_t m = (int16_t)(1 << (mag_bits - 1));
+                    if (kk < m) kk = (int16_t)(kk + (int16_t)((int16_t)(~0u << mag_bits) + 1));
+                    if (kk >= -128 && kk <= 127) p.ac_lookup[i] = (int16_t)((kk << 10) + (run << 4) + (len + mag_bits));
+                }
+            }
+        }
+        p.has_ac_lookup = true;
+    }
+    if (is_dc)
+        for (size_t i = 0; i < num_symbols; i++)
+            if (p.values[i] > 15) FAIL(ZJ_DE_HUFFMAN_DECODE, "Bad Huffman Table");
+}
+
+// ------------------------------------------------------------------------------------------------ bit reader
+struct BitStream {  // src/bitstream.rs:94-114
+    uint64_t buffer = 0, aligned_buffer = 0;
+    uint8_t bits_left = 0;
+    bool has_marker = false;
+    Marker marker{};
+    uint8_t successive_high = 0, successive_low = 0, spec_start = 0, spec_end = 0;
+    int32_t eob_run = 0;
+
+    static bool has_byte_ff(uint32_t b)  // has_byte(b, 255), bitstream.rs:705-717
+    {
+        const uint32_t v = b ^ 0xFFFFFFFFu;
+        return (~((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) | 0x7F7F7F7Fu)) != 0;
+    }
+    // bitstream.rs:159-261
+    void refill(Cursor &r)
+    {
+        if (bits_left <= 32 && !has_marker) {
+            const size_t position = r.pos;
+            if (position + 4 < r.len) {
+                const uint32_t msb = ((uint32_t)r.data[position] << 24) | ((uint32_t)r.data[position + 1] << 16) |
+                                     ((uint32_t)r.data[position + 2] << 8) | r.data[position + 3];
+                if (!has_byte_ff(msb)) {
+                    r.pos = position + 4;
+                    bits_left += 32;
+                    buffer <<= 32;
+                    buffer |= msb;
+                    aligned_buffer = buffer << (64 - bits_left);
+                    return;
+                }
+            }
+            for (int k = 0; k < 4; k++) {
+                const uint64_t byte = r.read_u8_or_zero();
+                buffer = (buffer << 8) | byte;
+                bits_left += 8;
+                if (byte == 0xff) {
+                    uint64_t next = r.read_u8_or_zero();
+                    if (next != 0x00) {
+                        while (next == 0xFF) next = r.read_u8_or_zero();
+                        if (next != 0x00) {
+                            buffer >>= 8;
+                            bits_left -= 8;
+                            if (bits_left != 0) aligned_buffer = buffer << (64 - bits_left);
+                            Marker m;
+                            if (!marker_from_u8((uint8_t)next, &m)) FAIL(ZJ_DE_FORMAT, fmt("Unknown marker 0xFF%llX", (unsigned long long)next));
+                            marker = m;
+                            has_marker = true;
+                            return;
+                        }
+                    }
+                }
+            }
+            aligned_buffer = buffer << (64 - bits_left);
+        } else if (has_marker) {
+            bits_left = 63;  // fake zero bits after a marker, bitstream.rs:254-258
+        }
+    }
+    template <int N> int32_t peek_bits() const { return (int32_t)(aligned_buffer >> (64 - N)); }
+    void drop_bits(uint8_t n)
+    {
+        bits_left = bits_left > n ? bits_left - n : 0;
+        aligned_buffer = n >= 64 ? 0 : aligned_buffer << n;
+    }
+    int32_t get_bits(uint8_t n)  // bitstream.rs:394-402 (a rotate, not a shift)
+    {
+        const uint64_t mask = (1ull << n) - 1;
+        const unsigned r = n & 63;
+        aligned_buffer = r ? (aligned_buffer << r) | (aligned_buffer >> (64 - r)) : aligned_buffer;
+        const int32_t bits = (int32_t)(aligned_buffer & mask);
+        bits_left = bits_left > n ? bits_left - n : 0;
+        return bits;
+    }
+    uint8_t get_bit() { const uint8_t k = (uint8_t)(aligned_buffer >> 63); drop_bits(1); return k; }
+    static int32_t huff_extend(int32_t x, int32_t s)  // bitstream.rs:685-689
+    {
+        return x + (((x - (1 << (s - 1))) >> 31) & (int32_t)(((uint32_t)-1 << s) + 1));
+    }
+    // decode_huff! macro, bitstream.rs:49-90
+    void decode_huff(int32_t &symbol, const HuffmanTable &t)
+    {
+        int32_t code_length = symbol >> HUFF_LOOKAHEAD;
+        symbol &= (1 << HUFF_LOOKAHEAD) - 1;
+        if (code_length > HUFF_LOOKAHEAD) {
+            symbol = peek_bits<16>();
+            while (code_length < 17) {
+                if (symbol < t.maxcode[code_length]) break;
+                code_length++;
+            }
+            if (code_length == 17) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("Bad Huffman Code 0x%X, corrupt JPEG", (unsigned)symbol));
+            symbol >>= (16 - code_length);
+            symbol = t.values[(symbol + t.offset[code_length]) & 0xFF];
+        }
+        drop_bits((uint8_t)code_length);
+    }
+    void decode_dc(Cursor &r, const HuffmanTable &dc, int32_t &pred)  // bitstream.rs:272-297
+    {
+        if (bits_left < 16) refill(r);
+        int32_t symbol = dc.lookup[peek_bits<HUFF_LOOKAHEAD>()];
+        decode_huff(symbol, dc);
+        if (symbol != 0) { const int32_t rr = get_bits((uint8_t)symbol); symbol = huff_extend(rr, symbol); }
+        pred = (int32_t)((uint32_t)pred + (uint32_t)symbol);
+    }
+    // bitstream.rs:314-373
+    void decode_mcu_block(Cursor &r, const HuffmanTable &dc, const HuffmanTable &ac, int16_t *block, int32_t &pred)
+    {
+        size_t pos = 1;
+        decode_dc(r, dc, pred);
+        block[0] = (int16_t)pred;
+        while (pos < 64) {
+            refill(r);
+            int32_t symbol = peek_bits<HUFF_LOOKAHEAD>();
+            const int16_t fast_ac = ac.ac_lookup[symbol];
+            symbol = ac.lookup[symbol];
+            if (fast_ac != 0) {
+                pos += (size_t)((fast_ac >> 4) & 63);
+                block[UN_ZIGZAG[std::min<size_t>(pos, 63)] & 63] = (int16_t)(fast_ac >> 10);
+                drop_bits((uint8_t)(fast_ac & 15));
+                pos += 1;
+            } else {
+                decode_huff(symbol, ac);
+                int32_t rr = symbol >> 4;
+                symbol &= 15;
+                if (symbol != 0) {
+                    pos += (size_t)rr;
+                    rr = get_bits((uint8_t)symbol);
+                    symbol = huff_extend(rr, symbol);
+                    block[UN_ZIGZAG[pos & 63] & 63] = (int16_t)symbol;
+                    pos += 1;
+                } else if (rr != 15) {
+                    return;
+                } else {
+                    pos += 16;
+                }
+            }
+        }
+    }
+    void decode_prog_dc_first(Cursor &r, const HuffmanTable &dc, int16_t *block, int32_t &pred)  // bitstream.rs:407-415
+    {
+        decode_dc(r, dc, pred);
+        *block = (int16_t)((uint16_t)(int16_t)pred * (uint16_t)(1u << successive_low));
+    }
+    void decode_prog_dc_refine(Cursor &r, int16_t *block)  // bitstream.rs:417-433
+    {
+        if (bits_left < 1) refill(r);
+        if (get_bit() == 1) *block = (int16_t)((uint16_t)*block + (uint16_t)(1u << successive_low));
+    }
+    // bitstream.rs:443-506
+    void decode_mcu_ac_first(Cursor &r, const HuffmanTable &ac, int16_t *block)
+    {
+        const int shift = successive_low;
+        size_t k = spec_start;
+        for (;;) {
+            refill(r);
+            int32_t symbol = peek_bits<HUFF_LOOKAHEAD>();
+            const int16_t fac = ac.ac_lookup[symbol];
+            symbol = ac.lookup[symbol];
+            if (fac != 0) {
+                k += (size_t)((fac >> 4) & 63);
+                block[UN_ZIGZAG[std::min<size_t>(k, 63)] & 63] = (int16_t)((uint16_t)(int16_t)(fac >> 10) * (uint16_t)(1u << shift));
+                drop_bits((uint8_t)(fac & 15));
+                k += 1;
+            } else {
+                decode_huff(symbol, ac);
+                int32_t rr = symbol >> 4;
+                symbol &= 15;
+                if (symbol != 0) {
+                    k += (size_t)rr;
+                    rr = get_bits((uint8_t)symbol);
+                    symbol = huff_extend(rr, symbol);
+                    block[UN_ZIGZAG[k & 63] & 63] = (int16_t)((uint16_t)(int16_t)symbol * (uint16_t)(1u << shift));
+                    k += 1;
+                } else {
+                    if (rr != 15) {
+                        eob_run = 1 << rr;
+                        eob_run += get_bits((uint8_t)rr);
+                        eob_run -= 1;
+                        break;
+                    }
+                    k += 16;
+                }
+            }
+            if (k > spec_end) break;
+        }
+    }
+    // bitstream.rs:507-658
+    void decode_mcu_ac_refine(Cursor &r, const HuffmanTable &table, int16_t *block)
+    {
+        const int16_t bit = (int16_t)(1 << successive_low);
+        uint8_t k = spec_start;
+        if (eob_run == 0) {
+            for (;;) {
+                refill(r);
+                int32_t symbol = table.lookup[peek_bits<HUFF_LOOKAHEAD>()];
+                decode_huff(symbol, table);
+                int32_t rr = symbol >> 4;
+                symbol &= 15;
+                if (symbol == 0) {
+                    if (rr != 15) {
+                        eob_run = 1 << rr;
+                        eob_run += get_bits((uint8_t)rr);
+                        break;
+                    }
+                } else {
+                    if (symbol != 1) FAIL(ZJ_DE_HUFFMAN_DECODE, "Bad Huffman code, corrupt JPEG?");
+                    symbol = get_bit() == 1 ? (int32_t)bit : (int32_t)-bit;
+                }
+                while (k <= spec_end) {
+                    int16_t *coefficient = &block[UN_ZIGZAG[k & 63] & 63];
+                    if (*coefficient != 0) {
+                        if (get_bit() == 1 && (*coefficient & bit) == 0) {
+                            if (*coefficient >= 0) *coefficient = (int16_t)(*coefficient + bit);
+                            else *coefficient = (int16_t)(*coefficient - bit);
+                        }
+                        if (bits_left < 1) refill(r);
+                    } else {
+                        rr -= 1;
+                        if (rr < 0) break;
+                    }
+                    k += 1;
+                }
+                if (symbol != 0) block[UN_ZIGZAG[k & 63] & 63] = (int16_t)symbol;
+                k += 1;
+                if (k > spec_end) break;
+            }
+        }
+        if (eob_run > 0) {
+            bool any = false;
+            for (int i = 1; i < 64; i++) if (block[i] != 0) { any = true; break; }
+            if (any) {
+                refill(r);
+                while (k <= spec_end) {
+                    int16_t *coefficient = &block[UN_ZIGZAG[k & 63] & 63];
+                    if (*coefficient != 0 && get_bit() == 1) {
+                        if ((*coefficient & bit) == 0) {
+                            if (*coefficient >= 0) *coefficient = (int16_t)(*coefficient + bit);
+                            else *coefficient = (int16_t)(*coefficient - bit);
+                        }
+                    }
+                    if (bits_left < 1) refill(r);
+                    k += 1;
+                }
+            }
+            eob_run -= 1;
+        }
+    }
+    void update_progressive_params(uint8_t ah, uint8_t al, uint8_t ss, uint8_t se) { successive_high = ah; successive_low = al; spec_start = ss; spec_end = se; }
+    void reset() { bits_left = 0; has_marker = false; buffer = 0; aligned_buffer = 0; eob_run = 0; }  // bitstream.rs:673-680
+};
+
+// ------------------------------------------------------------------------------------------------ decoder
+enum ComponentID { ID_Y, ID_CB, ID_CR };
+static const char *comp_debug(int id) { return id == ID_Y ? "Y" : (id == ID_CB ? "Cb" : "Cr"); }
+enum SubSamp { SS_NONE, SS_H, SS_V, SS_HV };
+
+struct Component {  // src/components.rs:18-43
+    int component_id;
+    size_t vertical_sample, horizontal_sample, dc_huff_table, ac_huff_table;
+    uint8_t quantization_table_number;
+    int32_t quantization_table[64];
+    int32_t dc_pred;
+    size_t width_stride;
+    uint8_t id;
+};
+
+struct PlaneBuf {
+    int16_t *p = nullptr;
+    size_t cap = 0;   // i16
+    bool pinned = false;
+    void release()
+    {
+        if (!p) return;
+        if (pinned) cudaFreeHost(p); else free(p);
+        p = nullptr; cap = 0;
+    }
+    int16_t *ensure_zeroed(size_t n, bool want_pinned)
+    {
+        if (n > cap) {
+            release();
+            size_t want = n + n / 8 + 64;
+            if (want_pinned && cudaHostAlloc((void **)&p, want * 2, cudaHostAllocPortable) == cudaSuccess) pinned = true;
+            else { cudaGetLastError(); p = (int16_t *)aligned_alloc(64, (want * 2 + 63) & ~(size_t)63); pinned = false; }
+            if (!p) FAIL(ZJ_DE_FORMAT, "out of memory for coefficient planes");
+            cap = want;
+        }
+        memset(p, 0, n * 2);
+        return p;
+    }
+};
+
+}  // namespace
+
+struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
+    zj_options options;
+    zj_image_info info{};
+    bool qt_present[4] = {false, false, false, false};
+    int32_t qt_tables[4][64];
+    HuffmanTable dc_tables[4], ac_tables[4];
+    std::vector<Component> components;
+    size_t h_max = 1, v_max = 1, mcu_width = 0, mcu_height = 0, mcu_x = 0, mcu_y = 0;
+    bool interleaved = false;
+    int sub_sample_ratio = SS_NONE;
+    uint32_t input_colorspace = ZJ_CS_YCBCR;
+    bool is_progressive = false;
+    uint8_t spec_start = 0, spec_end = 0, succ_high = 0, succ_low = 0, num_scans = 0;
+    size_t z_order[4] = {0, 0, 0, 0};
+    size_t restart_interval = 0, todo = 0x7fffffff;
+    // error of the last call
+    int err_kind = ZJ_DE_NONE;
+    std::string err_msg, err_display;
+    // coefficient planes (reused across calls)
+    PlaneBuf planes[3];
+    size_t plane_len[3] = {0, 0, 0};
+    bool have_device = false;
+
+    explicit zj_decoder(const zj_options &o) : options(o)
+    {
+        for (auto &t : dc_tables) t.present = false;
+        for (auto &t : ac_tables) t.present = false;
+        int n = 0;
+        have_device = cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+        if (!have_device) cudaGetLastError();
+    }
+    ~zj_decoder() { for (auto &p : planes) p.release(); }
+
+    void reset_state()  // a fresh Decoder::default(options) for every call, keeping the plane buffers
+    {
+        const uint32_t keep_cs = user_out_cs;
+        options.out_colorspace = keep_cs;
+        info = zj_image_info{};
+        for (bool &b : qt_present) b = false;
+        for (auto &t : dc_tables) t.present = false;
+        for (auto &t : ac_tables) t.present = false;
+        components.clear();
+        h_max = v_max = 1;
+        mcu_width = mcu_height = mcu_x = mcu_y = 0;
+        interleaved = false;
+        sub_sample_ratio = SS_NONE;
+        input_colorspace = ZJ_CS_YCBCR;
+        is_progressive = false;
+        spec_start = spec_end = succ_high = succ_low = num_scans = 0;
+        for (auto &z : z_order) z = 0;
+        restart_interval = 0;
+        todo = 0x7fffffff;
+    }
+    uint32_t user_out_cs = ZJ_CS_RGB;
+
+    static size_t out_components(uint32_t cs)
+    {
+        switch (cs) {
+        case ZJ_CS_RGB: case ZJ_CS_YCBCR: return 3;
+        case ZJ_CS_GRAYSCALE: return 1;
+        default: return 4;
+        }
+    }
+    size_t in_components() const { return input_colorspace == ZJ_CS_GRAYSCALE ? 1 : 3; }
+
+    // ---------------------------------------------------------------- headers (src/headers.rs)
+    void parse_huffman(Cursor &buf)  // headers.rs:18-121
+    {
+        size_t avail = buf.pos < buf.len ? buf.len - buf.pos : 0;
+        if (avail < 2) { buf.pos += avail; FAIL(ZJ_DE_FORMAT_STATIC, "Could not read Huffman length from image"); }
+        const uint16_t l = buf.read_u16_be();
+        if (l < 2) FAIL(ZJ_DE_FORMAT_STATIC, "Invalid Huffman length in image");
+        int32_t dht_length = (int32_t)l - 2;
+        while (dht_length > 16) {
+            const uint8_t ht_info = buf.read_byte();
+            const uint8_t dc_or_ac = (ht_info >> 4) & 0xF;
+            const size_t index = ht_info & 0xF;
+            uint8_t num_symbols[17] = {0};
+            if (index >= 4) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("Invalid DHT index %zu, expected between 0 and 3", index));
+            if (dc_or_ac > 1) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("Invalid DHT position %u, should be 0 or 1", (unsigned)dc_or_ac));
+            buf.read_exact(num_symbols + 1, 16, ZJ_DE_HUFFMAN_DECODE, "Could not read bytes into the buffer");
+            dht_length -= 1 + 16;
+            int32_t symbols_sum = 0;
+            for (int i = 0; i < 17; i++) symbols_sum += num_symbols[i];
+            if (symbols_sum > 256) FAIL(ZJ_DE_HUFFMAN_DECODE, "Encountered Huffman table with excessive length in DHT");
+            if (symbols_sum > dht_length)
+                FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("Excessive Huffman table of length %d found when header length is %d", symbols_sum, dht_length));
+            dht_length -= symbols_sum;
+            uint8_t symbols[256] = {0};
+            buf.read_exact(symbols, (size_t)symbols_sum, ZJ_DE_FORMAT, "Could not read symbols into the buffer\nfailed to fill whole buffer");
+            if (dc_or_ac == 0) build_huffman(dc_tables[index], num_symbols, symbols, true, is_progressive);
+            else build_huffman(ac_tables[index], num_symbols, symbols, false, is_progressive);
+        }
+        if (dht_length > 0) FAIL(ZJ_DE_HUFFMAN_DECODE, "Bogus Huffman table definition");
+    }
+    void parse_dqt(Cursor &buf)  // headers.rs:125-196
+    {
+        uint16_t l;
+        try { l = buf.read_u16_be(); } catch (DecodeError &) { FAIL(ZJ_DE_FORMAT, "Could not read  DQT length Exhausted data in the image"); }
+        if (l < 2) FAIL(ZJ_DE_DQT_ERROR, "Invalid DQT length. Length should be greater than 2");
+        uint16_t qt_length = (uint16_t)(l - 2);
+        while (qt_length > 0) {
+            const uint8_t qt_info = buf.read_byte();
+            const size_t precision = qt_info >> 4, table_position = qt_info & 0x0f;
+            const size_t precision_value = 64 * (precision + 1);
+            if ((uint16_t)(precision_value + 1) > qt_length)
+                FAIL(ZJ_DE_DQT_ERROR, fmt("Invalid QT table bytes left :%u. Too small to construct a valid qt table which should be %zu long", (unsigned)qt_length, precision_value + 1));
+            int32_t table[64];
+            if (precision == 0) {
+                uint8_t qv[64];
+                buf.read_exact(qv, 64, ZJ_DE_FORMAT, "Could not read symbols into the buffer\nfailed to fill whole buffer");
+                qt_length = (uint16_t)(qt_length - (uint16_t)precision_value - 1);
+                for (int i = 0; i < 64; i++) table[UN_ZIGZAG[i]] = qv[i];  // un_zig_zag, headers.rs:533-543
+            } else if (precision == 1) {
+                FAIL(ZJ_DE_DQT_ERROR, "Support for 16 bit quantization table is not complete");
+            } else {
+                FAIL(ZJ_DE_DQT_ERROR, fmt("Expected QT precision value of either 0 or 1, found %zu", precision));
+            }
+            if (table_position >= 4) FAIL(ZJ_DE_DQT_ERROR, fmt("Too large table position for QT :%zu, expected between 0 and 3", table_position));
+            memcpy(qt_tables[table_position], table, sizeof(table));
+            qt_present[table_position] = true;
+        }
+    }
+    void parse_start_of_frame(Cursor &buf, int sof)  // headers.rs:200-347
+    {
+        uint16_t length;
+        try { length = buf.read_u16_be(); } catch (DecodeError &) { FAIL(ZJ_DE_FORMAT, "Cannot read SOF length, exhausted data"); }
+        const uint8_t dt_precision = buf.read_byte();
+        if (dt_precision != 8)
+            FAIL(ZJ_DE_SOF_ERROR, fmt("The library can only parse 8-bit images, the image has %u bits of precision", (unsigned)dt_precision));
+        info.pixel_density = dt_precision;
+        uint16_t img_height, img_width;
+        try { img_height = buf.read_u16_be(); } catch (DecodeError &) { FAIL(ZJ_DE_FORMAT, "Cannot read image height, exhausted data"); }
+        info.height = img_height;
+        try { img_width = buf.read_u16_be(); } catch (DecodeError &) { FAIL(ZJ_DE_FORMAT, "Cannot read image width, exhausted data"); }
+        info.width = img_width;
+        info.valid = 1;
+        if (img_width > (uint16_t)options.max_width)
+            FAIL(ZJ_DE_FORMAT, fmt("Image width %u greater than width limit %u. If use `set_limits` if you want to support huge images", (unsigned)img_width, (unsigned)(uint16_t)options.max_width));
+        if (img_height > (uint16_t)options.max_height)
+            FAIL(ZJ_DE_FORMAT, fmt("Image height %u greater than height limit %u. If use `set_limits` if you want to support huge images", (unsigned)img_height, (unsigned)(uint16_t)options.max_height));
+        if (img_width == 0 || img_height == 0) FAIL(ZJ_DE_ZERO_ERROR, "");
+        const uint8_t num_components = buf.read_byte();
+        if (num_components == 0) FAIL(ZJ_DE_SOF_ERROR, "Number of components cannot be zero.");
+        const uint16_t expected = (uint16_t)(8 + 3 * (uint16_t)num_components);
+        if (length != expected)
+            FAIL(ZJ_DE_SOF_ERROR, fmt("Length of start of frame differs from expected %u,value is %u", (unsigned)expected, (unsigned)length));
+        if (num_components == 1) { input_colorspace = ZJ_CS_GRAYSCALE; options.out_colorspace = ZJ_CS_GRAYSCALE; }
+        info.components = num_components;
+        std::vector<Component> comps;
+        for (int i = 0; i < num_components; i++) {
+            uint8_t a[3];
+            buf.read_exact(a, 3, ZJ_DE_FORMAT, "Could not read component data\nfailed to fill whole buffer");
+            Component c{};  // Components::from, components.rs:49-114
+            if (a[0] == 1) c.component_id = ID_Y;
+            else if (a[0] == 2) c.component_id = ID_CB;
+            else if (a[0] == 3) c.component_id = ID_CR;
+            else FAIL(ZJ_DE_FORMAT, fmt("Unknown component id found,%u, expected value between 1 and 3\nNote I and Q components are not supported yet", (unsigned)a[0]));
+            c.horizontal_sample = a[1] >> 4;
+            c.vertical_sample = a[1] & 0x0f;
+            c.quantization_table_number = a[2];
+            if (a[2] >= 4) FAIL(ZJ_DE_FORMAT, fmt("Too large quantization number :%u, expected value between 0 and 4", (unsigned)a[2]));
+            auto pow2 = [](size_t x) { return x != 0 && (x & (x - 1)) == 0; };
+            if (!pow2(c.horizontal_sample)) FAIL(ZJ_DE_FORMAT, fmt("Horizontal sample is not a power of two(%zu) cannot decode", c.horizontal_sample));
+            if (!pow2(c.vertical_sample)) FAIL(ZJ_DE_FORMAT, fmt("Vertical sub-sample is not power of two(%zu) cannot decode", c.vertical_sample));
+            c.width_stride = c.horizontal_sample;
+            c.id = a[0];
+            comps.push_back(c);
+        }
+        info.sof = (uint8_t)sof;
+        for (auto &c : comps) {  // headers.rs:306-339 (h_max / mcu_x evolve component by component)
+            h_max = std::max(h_max, c.horizontal_sample);
+            v_max = std::max(v_max, c.vertical_sample);
+            mcu_width = h_max * 8;
+            mcu_height = v_max * 8;
+            mcu_x = ((size_t)info.width + mcu_width - 1) / mcu_width;
+            mcu_y = ((size_t)info.height + mcu_height - 1) / mcu_height;
+            if (h_max != 1 || v_max != 1) interleaved = true;
+            if (!qt_present[c.quantization_table_number])
+                FAIL(ZJ_DE_DQT_ERROR, fmt("No quantization table for component %s", comp_debug(c.component_id)));
+            memcpy(c.quantization_table, qt_tables[c.quantization_table_number], sizeof(c.quantization_table));
+            c.width_stride *= mcu_x * 8;
+        }
+        for (bool &b : qt_present) b = false;  // headers.rs:343
+        components = comps;
+    }
+    void parse_sos(Cursor &buf)  // headers.rs:350-463
+    {
+        const uint16_t ls = buf.read_u16_be();
+        const uint8_t ns = buf.read_byte();
+        bool seen[4] = {false, false, false, false};
+        num_scans = ns;
+        if (ls != 6 + 2 * (uint16_t)ns) FAIL(ZJ_DE_SOS_ERROR, "Bad SOS length,corrupt jpeg");
+        if (!(ns >= 1 && ns < 4))
+            FAIL(ZJ_DE_SOS_ERROR, fmt("Number of components in start of scan should be less than 3 but more than 0. Found %u", (unsigned)ns));
+        if (info.components == 0) FAIL(ZJ_DE_SOF_ERROR, "Number of components cannot be zero.");
+        for (int i = 0; i < ns; i++) {
+            const uint8_t id = buf.read_byte();
+            if ((size_t)id > components.size())
+                FAIL(ZJ_DE_SOF_ERROR, fmt("Too large component ID %u, expected value between 0 and %zu", (unsigned)id, components.size()));
+            if (id >= 4) FAIL(ZJ_DE_SOF_ERROR, fmt("Too large component ID %u, expected value between 0 and %zu", (unsigned)id, components.size()));
+            if (seen[id]) FAIL(ZJ_DE_SOF_ERROR, fmt("Duplicate ID %u seen twice in the same component", (unsigned)id));
+            seen[id] = true;
+            const uint8_t y = buf.read_byte();
+            uint8_t j = 0;
+            while (j < info.components) {
+                if (components[j].id == id) break;
+                j++;
+            }
+            if (j == info.components)
+                FAIL(ZJ_DE_SOF_ERROR, fmt("Invalid component id %u, expected a value between 0 and %zu", (unsigned)id, components.size()));
+            components[j].dc_huff_table = (y >> 4) & 0xF;
+            components[j].ac_huff_table = y & 0xF;
+            z_order[i] = j;
+        }
+        spec_start = buf.read_byte() & 63;
+        spec_end = buf.read_byte() & 63;
+        const uint8_t bit_approx = buf.read_byte();
+        succ_high = bit_approx >> 4;
+        if (succ_high > 13) FAIL(ZJ_DE_SOF_ERROR, fmt("Invalid Ah parameter %u, range should be 0-13", (unsigned)succ_low));
+        succ_low = bit_approx & 0xF;
+        if (succ_low > 13) FAIL(ZJ_DE_SOF_ERROR, fmt("Invalid Al parameter %u, range should be 0-13", (unsigned)succ_low));
+    }
+    void skip_segment(Cursor &buf, const char *msg_fmt)
+    {
+        const uint16_t length = buf.read_u16_be();
+        if (length < 2) FAIL(ZJ_DE_FORMAT, fmt(msg_fmt, (unsigned)length));
+        buf.consume((size_t)length - 2);
+    }
+    void parse_marker_inner(const Marker &m, Cursor &buf)  // decoder.rs:304-411
+    {
+        switch (m.kind) {
+        case M_SOF:
+            if (m.n == 2) is_progressive = true;
+            parse_start_of_frame(buf, m.n == 0 ? 0 : 2);
+            break;
+        case M_DQT: parse_dqt(buf); break;
+        case M_DHT: parse_huffman(buf); break;
+        case M_SOS: parse_sos(buf); break;
+        case M_EOI: FAIL(ZJ_DE_FORMAT, "Premature End of image");
+        case M_DAC: case M_DNL:
+            FAIL(ZJ_DE_FORMAT, fmt("Parsing of the following header `%s` is not supported,cannot continue", marker_debug(m).c_str()));
+        case M_DRI:
+            if (buf.read_u16_be() != 4) FAIL(ZJ_DE_FORMAT, "Bad DRI length, Corrupt JPEG");
+            restart_interval = buf.read_u16_be();
+            todo = restart_interval;
+            break;
+        default: skip_segment(buf, "Found a marker with invalid length:%u\n"); break;
+        }
+    }
+    void decode_headers_internal(Cursor &buf)  // decoder.rs:239-303
+    {
+        const uint16_t magic = buf.read_u16_be();
+        uint8_t last_byte = 0;
+        size_t bytes_before_marker = 0;
+        if (magic != 0xffd8) FAIL(ZJ_DE_ILLEGAL_MAGIC_BYTES, fmt("%u", (unsigned)magic));
+        for (;;) {
+            const uint8_t m = buf.read_byte();
+            if (last_byte == 0xFF) {
+                Marker mk;
+                bytes_before_marker = 0;
+                if (marker_from_u8(m, &mk)) {
+                    parse_marker_inner(mk, buf);
+                    if (mk.kind == M_SOS) return;
+                } else {
+                    skip_segment(buf, "Found a marker with invalid length : %u");
+                }
+            }
+            last_byte = m;
+            bytes_before_marker += 1;
+            if (options.strict_mode && bytes_before_marker > 3) FAIL(ZJ_DE_FORMAT_STATIC, "[strict-mode]: Extra bytes between headers");
+        }
+    }
+
+    // ---------------------------------------------------------------- checks (decoder.rs:468-523,609-646; mcu.rs:74-116)
+    void check_component_dimensions()
+    {
+        const Component *y = nullptr;
+        for (auto &c : components) if (c.component_id == ID_Y) { y = &c; break; }
+        if (!y) FAIL(ZJ_DE_FORMAT_STATIC, "Could not find Y component for the image");
+        const size_t cbcr = y->width_stride / h_max;
+        for (auto &c : components) {
+            if (c.component_id == ID_Y) continue;
+            if (c.width_stride != cbcr)
+                FAIL(ZJ_DE_FORMAT, fmt("Invalid image width and height stride for component %s, expected %zu, but found %zu", comp_debug(c.component_id), cbcr, c.width_stride));
+            if (c.horizontal_sample != 1 || c.vertical_sample != 1)
+                FAIL(ZJ_DE_FORMAT, fmt("Invalid component sample for component %s, expected (1,1), found (%zu,%zu)", comp_debug(c.component_id), c.vertical_sample, c.horizontal_sample));
+        }
+    }
+    void check_tables()
+    {
+        for (size_t i = 0; i < in_components() && i < components.size(); i++) {
+            const Component &c = components[i];
+            if (c.dc_huff_table >= 4) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No Huffman DC table for component %s ", comp_debug(c.component_id)));
+            if (!dc_tables[c.dc_huff_table].present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No DC table for component %s", comp_debug(c.component_id)));
+            if (c.ac_huff_table >= 4) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No Huffman AC table for component %s ", comp_debug(c.component_id)));
+            if (!ac_tables[c.ac_huff_table].present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No AC table for component %s", comp_debug(c.component_id)));
+        }
+    }
+    void set_upsampling()
+    {
+        if (h_max == v_max && h_max == 1) return;
+        if (h_max == 2 && v_max == 1) sub_sample_ratio = SS_H;
+        else if (h_max == 1 && v_max == 2) sub_sample_ratio = SS_V;
+        else if (h_max == 2 && v_max == 2) sub_sample_ratio = SS_HV;
+        else FAIL(ZJ_DE_FORMAT, "Unknown down-sampling method, cannot continue");
+    }
+    void handle_rst(BitStream &stream)  // mcu.rs:386-418
+    {
+        todo = restart_interval;
+        if (stream.has_marker) {
+            if (stream.marker.kind == M_RST) {
+                stream.reset();
+                for (auto &c : components) c.dc_pred = 0;
+            } else if (stream.marker.kind == M_EOI) {
+            } else {
+                FAIL(ZJ_DE_MCU_ERROR, fmt("Marker %s found in bitstream, possibly corrupt jpeg", marker_debug(stream.marker).c_str()));
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- baseline entropy stage (mcu.rs:127-351)
+    void decode_baseline(Cursor &reader)
+    {
+        check_component_dimensions();
+        check_tables();
+        if (components.size() < in_components()) FAIL(ZJ_DE_FORMAT, "missing components");
+        size_t mcu_w, mcu_h, bias = 1;
+        if (interleaved) {
+            set_upsampling();
+            if (sub_sample_ratio == SS_H) { mcu_w = mcu_x * 2; mcu_h = mcu_y / 2; }
+            else if (sub_sample_ratio == SS_HV) { mcu_w = mcu_x; mcu_h = mcu_y / 2; bias = 2; }
+            else { mcu_w = mcu_x; mcu_h = mcu_y; }
+        } else {
+            mcu_w = ((size_t)info.width + 7) / 8;
+            mcu_h = ((size_t)info.height + 7) / 8;
+        }
+        if (input_colorspace == ZJ_CS_GRAYSCALE && interleaved) {  // mcu.rs:171-196
+            if (options.strict_mode) FAIL(ZJ_DE_FORMAT_STATIC, "[strict-mode]: Grayscale image with down-sampled component.");
+            mcu_w = ((size_t)info.width + 7) / 8;
+            h_max = 1;
+            options.out_colorspace = ZJ_CS_GRAYSCALE;
+            v_max = 1;
+            sub_sample_ratio = SS_NONE;
+            components[0].vertical_sample = 1;
+            components[0].width_stride = mcu_w * 8;
+            components[0].horizontal_sample = 1;
+            mcu_h = ((size_t)info.height + 7) / 8;
+            bias = 1;
+        }
+        const size_t component_capacity = mcu_w * 64;
+        const bool is_hv = sub_sample_ratio == SS_HV;
+        const size_t out_nc = out_components(options.out_colorspace);
+        const size_t width_stride = (component_capacity * components[0].vertical_sample * components[0].horizontal_sample * bias) >> 1;
+        const size_t hv_width_stride = width_stride >> 1;
+        // the reference's output Vec must have one chunk per strip, or chunks.next().unwrap() panics (mcu.rs:354)
+        {
+            const size_t capacity = (size_t)(uint16_t)(info.width + 8) * (size_t)(uint16_t)(info.height + 8);
+            const size_t extra = (interleaved ? 128u : 0u) * (size_t)info.height * out_nc;
+            const size_t chunk = (size_t)info.width * out_nc * 8 * h_max * v_max;
+            if (mcu_h > (capacity * out_nc + extra) / chunk) FAIL(ZJ_DE_GPU, "the reference decoder panics on this geometry (output chunks exhausted, mcu.rs:354)");
+        }
+        // whole-image planes: strip s of component z lives at s * strip_len[z] (== mcu_prog.rs layout)
+        size_t strip_len[3] = {0, 0, 0};
+        for (size_t pos = 0; pos < components.size() && pos < 3; pos++) {
+            plane_len[pos] = 0;
+            if (std::min(out_nc - 1, pos) == pos) {  // mcu.rs:244
+                strip_len[pos] = component_capacity * components[pos].vertical_sample * components[pos].horizontal_sample * bias;
+                plane_len[pos] = strip_len[pos] * mcu_h;
+                planes[pos].ensure_zeroed(plane_len[pos], have_device);
+            }
+        }
+        BitStream stream;
+        int16_t tmp[64];
+        for (size_t strip = 0; strip < mcu_h; strip++) {
+            for (size_t v = 0; v < bias; v++) {
+                for (size_t j = 0; j < mcu_w; j++) {
+                    for (size_t pos = 0; pos < in_components(); pos++) {
+                        Component &component = components[pos];
+                        const HuffmanTable &dc_table = dc_tables[component.dc_huff_table & 3];
+                        if (!dc_table.present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No DC table for component %s", comp_debug(component.component_id)));
+                        const HuffmanTable &ac_table = ac_tables[component.ac_huff_table & 3];
+                        if (!ac_table.present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No AC table for component %s", comp_debug(component.component_id)));
+                        for (size_t v_samp = 0; v_samp < component.vertical_sample; v_samp++) {
+                            for (size_t h_samp = 0; h_samp < component.horizontal_sample; h_samp++) {
+                                if (std::min(out_nc - 1, pos) == pos) {
+                                    // mcu.rs:293-312
+                                    const size_t is_y = component.component_id == ID_Y ? 1 : 0;
+                                    const size_t y_offset = is_y * v * (hv_width_stride + (hv_width_stride * (component.vertical_sample - 1)));
+                                    const size_t another_stride = (width_stride * v_samp * (is_hv ? 0 : 1)) + hv_width_stride * v_samp * (is_hv ? 1 : 0);
+                                    const size_t yet_another_stride = (is_hv ? 1 : 0) * (width_stride >> 2) * v * (component.component_id != ID_Y ? 1 : 0);
+                                    const size_t start = (j * 64 * component.horizontal_sample) + (h_samp * 64) + another_stride + y_offset + yet_another_stride;
+                                    if (start + 64 > strip_len[pos]) FAIL(ZJ_DE_GPU, "the reference decoder panics here (block index out of range, mcu.rs:314)");
+                                    stream.decode_mcu_block(reader, dc_table, ac_table, planes[pos].p + strip * strip_len[pos] + start, component.dc_pred);
+                                } else {
+                                    stream.decode_mcu_block(reader, dc_table, ac_table, tmp, component.dc_pred);
+                                }
+                            }
+                        }
+                        todo = todo - 1;  // wrapping_sub, once per COMPONENT (Q8)
+                        if (todo == 0) handle_rst(stream);
+                        if (stream.has_marker) {  // mcu.rs:337-348
+                            if (stream.marker.kind == M_EOI) break;
+                            if (stream.marker.kind == M_RST) continue;
+                            parse_marker_inner(stream.marker, reader);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- progressive entropy stage (mcu_prog.rs)
+    bool get_marker(Cursor &reader, BitStream &stream, Marker *out)  // mcu_prog.rs:436-473
+    {
+        if (stream.has_marker) { stream.has_marker = false; *out = stream.marker; return true; }
+        for (;;) {
+            if (reader.pos >= reader.len) return false;
+            const uint8_t marker = reader.data[reader.pos++];
+            if (marker == 255) {
+                if (reader.pos >= reader.len) return false;
+                uint8_t r = reader.data[reader.pos++];
+                while (r == 0xFF) {
+                    if (reader.pos >= reader.len) return false;
+                    r = reader.data[reader.pos++];
+                }
+                if (r != 0) return marker_from_u8(r, out);
+                if (reader.pos >= reader.len) return false;
+            }
+        }
+    }
+    void parse_entropy_coded_data(Cursor &reader, BitStream &stream)  // mcu_prog.rs:249-430
+    {
+        check_component_dimensions();
+        stream.reset();
+        for (auto &c : components) c.dc_pred = 0;
+        if ((size_t)num_scans > in_components())
+            FAIL(ZJ_DE_FORMAT, fmt("Number of scans %u cannot be greater than number of components, %zu", (unsigned)num_scans, in_components()));
+        if (num_scans == 1) {
+            if (spec_end != 0 && spec_start == 0) FAIL(ZJ_DE_HUFFMAN_DECODE, "Can't merge DC and AC corrupt jpeg");
+            const size_t k = z_order[0];
+            if (k >= components.size()) FAIL(ZJ_DE_FORMAT, fmt("Cannot find component %zu, corrupt image", k));
+            size_t mw, mh;
+            if (components[k].component_id == ID_Y || !interleaved) { mw = ((size_t)info.width + 7) / 8; mh = ((size_t)info.height + 7) / 8; }
+            else { mw = mcu_x; mh = mcu_y; }
+            size_t i = 0, j = 0;
+            while (i < mh) {
+                while (j < mw) {
+                    const size_t start = 64 * (j + i * (components[k].width_stride / 8));
+                    if (i >= mh) break;
+                    if (k >= 3 || start + 64 > plane_len[k]) FAIL(ZJ_DE_GPU, "the reference decoder panics here (block index out of range, mcu_prog.rs:304)");
+                    int16_t *data = planes[k].p + start;
+                    if (spec_start == 0) {
+                        const size_t pos = components[k].dc_huff_table & 3;
+                        if (!dc_tables[pos].present) FAIL(ZJ_DE_FORMAT, fmt("Huffman table at index  %zu not initialized", pos));
+                        if (succ_high == 0) stream.decode_prog_dc_first(reader, dc_tables[pos], data, components[k].dc_pred);
+                        else stream.decode_prog_dc_refine(reader, data);
+                    } else {
+                        const size_t pos = components[k].ac_huff_table;
+                        if (pos >= 4) FAIL(ZJ_DE_FORMAT, fmt("No huffman table for component:%zu", pos));
+                        if (!ac_tables[pos].present) FAIL(ZJ_DE_FORMAT, fmt("Huffman table at index  %zu not initialized", pos));
+                        if (succ_high == 0) {
+                            if (stream.eob_run > 0) {  // skip whole blocks, mcu_prog.rs:336-351
+                                i += (j + (size_t)stream.eob_run - 1) / mw;
+                                j = (j + (size_t)stream.eob_run - 1) % mw;
+                                stream.eob_run = 0;
+                            } else {
+                                stream.decode_mcu_ac_first(reader, ac_tables[pos], data);
+                            }
+                        } else {
+                            stream.decode_mcu_ac_refine(reader, ac_tables[pos], data);
+                        }
+                    }
+                    j += 1;
+                    todo -= 1;
+                    if (todo == 0) handle_rst(stream);
+                }
+                j = 0;
+                i += 1;
+            }
+        } else {
+            if (spec_end != 0) FAIL(ZJ_DE_HUFFMAN_DECODE, "Can't merge dc and AC corrupt jpeg");
+            for (size_t i = 0; i < mcu_y; i++) {
+                for (size_t j = 0; j < mcu_x; j++) {
+                    for (size_t k = 0; k < num_scans; k++) {
+                        const size_t n = z_order[k];
+                        if (n >= components.size()) FAIL(ZJ_DE_FORMAT, fmt("Cannot find component %zu, corrupt image", n));
+                        Component &component = components[n];
+                        if (component.dc_huff_table >= 4) FAIL(ZJ_DE_FORMAT, fmt("No huffman table for component:%zu", component.dc_huff_table));
+                        const HuffmanTable &huff_table = dc_tables[component.dc_huff_table];
+                        if (!huff_table.present) FAIL(ZJ_DE_FORMAT, fmt("Huffman table at index  %zu not initialized", component.dc_huff_table));
+                        for (size_t v_samp = 0; v_samp < component.vertical_sample; v_samp++) {
+                            for (size_t h_samp = 0; h_samp < component.horizontal_sample; h_samp++) {
+                                const size_t x2 = j * component.horizontal_sample + h_samp;
+                                const size_t y2 = i * component.vertical_sample + v_samp;
+                                const size_t position = 64 * (x2 + y2 * component.width_stride / 8);
+                                if (n >= 3 || position >= plane_len[n]) FAIL(ZJ_DE_GPU, "the reference decoder panics here (block index out of range, mcu_prog.rs:408)");
+                                int16_t *data = planes[n].p + position;
+                                if (succ_high == 0) stream.decode_prog_dc_first(reader, huff_table, data, component.dc_pred);
+                                else stream.decode_prog_dc_refine(reader, data);
+                            }
+                        }
+                        todo = todo - 1;
+                        if (todo == 0) handle_rst(stream);
+                    }
+                }
+            }
+        }
+    }
+    void decode_progressive(Cursor &reader)  // mcu_prog.rs:49-129 (+ the geometry half of finish_progressive_decoding)
+    {
+        check_component_dimensions();
+        size_t mw, mh;
+        if (interleaved) { mw = mcu_x; mh = mcu_y; } else { mw = ((size_t)info.width + 7) / 8; mh = ((size_t)info.height + 7) / 8; }
+        mw *= 64;
+        if (components.size() < in_components()) FAIL(ZJ_DE_FORMAT, "missing components");
+        for (size_t i = 0; i < 3; i++) plane_len[i] = 0;
+        for (size_t i = 0; i < in_components(); i++) {
+            plane_len[i] = mw * components[i].vertical_sample * components[i].horizontal_sample * mh;
+            planes[i].ensure_zeroed(plane_len[i], have_device);
+        }
+        size_t seen_scans = 1;
+        BitStream stream;
+        stream.update_progressive_params(succ_high, succ_low, spec_start, spec_end);
+        parse_entropy_coded_data(reader, stream);
+        if (!stream.has_marker) FAIL(ZJ_DE_FORMAT_STATIC, "Marker missing where expected");
+        Marker marker = stream.marker;
+        stream.has_marker = false;
+        while (!(marker.kind == M_EOI)) {
+            if (marker.kind == M_DHT) {
+                parse_huffman(reader);
+            } else if (marker.kind == M_SOS) {
+                parse_sos(reader);
+                stream.update_progressive_params(succ_high, succ_low, spec_start, spec_end);
+                parse_entropy_coded_data(reader, stream);
+                if (!get_marker(reader, stream, &marker)) FAIL(ZJ_DE_FORMAT_STATIC, "Marker missing where expected");
+                seen_scans += 1;
+                if (seen_scans > options.max_scans) FAIL(ZJ_DE_FORMAT, fmt("Too many scans, exceeded limit of %u", (unsigned)options.max_scans));
+                stream.reset();
+                continue;
+            } else {
+                break;
+            }
+            if (!get_marker(reader, stream, &marker)) FAIL(ZJ_DE_FORMAT_STATIC, "Marker missing where expected");
+        }
+        // finish_progressive_decoding, mcu_prog.rs:132-168
+        set_upsampling();
+        if (input_colorspace == ZJ_CS_GRAYSCALE && interleaved) {
+            if (options.strict_mode) FAIL(ZJ_DE_FORMAT_STATIC, "[strict-mode]: Grayscale image with down-sampled component.");
+            // mcu_prog.rs:161-167 sets horizontal_sample = mcu_width ("not tested" per its own comment); the IDCT
+            // then indexes past its chunk and panics (idct get_mut(..).unwrap()).
+            FAIL(ZJ_DE_GPU, "the reference decoder panics on progressive grayscale images with a down-sampled component");
+        }
+    }
+
+    // ---------------------------------------------------------------- host stage driver
+    void fill_descriptor(zj_image *img)
+    {
+        memset(img, 0, sizeof(*img));
+        img->width = info.width;
+        img->height = info.height;
+        img->n_comp = (uint32_t)in_components();
+        img->out_cs = options.out_colorspace;
+        img->variant = options.use_unsafe ? ZJ_VARIANT_X86 : ZJ_VARIANT_SCALAR;
+        img->flags = is_progressive ? ZJ_FLAG_PROGRESSIVE : 0;
+        for (size_t z = 0; z < in_components(); z++) {
+            zj_component &c = img->comp[z];
+            c.coeff = plane_len[z] ? planes[z].p : nullptr;
+            c.n_i16 = plane_len[z];
+            memcpy(c.qt, components[z].quantization_table, sizeof(c.qt));
+            c.h_samp = (uint32_t)components[z].horizontal_sample;
+            c.v_samp = (uint32_t)components[z].vertical_sample;
+            c.width_stride = (uint32_t)components[z].width_stride;
+        }
+    }
+    void host_stage(const uint8_t *buf, size_t len, zj_image *img)  // decode_internal, decoder.rs:420-434
+    {
+        reset_state();
+        Cursor cur{buf, len, 0};
+        decode_headers_internal(cur);
+        if (is_progressive) decode_progressive(cur);
+        else decode_baseline(cur);
+        fill_descriptor(img);
+    }
+    void set_error(const DecodeError &e)
+    {
+        err_kind = e.kind;
+        err_msg = e.msg;
+        switch (e.kind) {  // Display, errors.rs:77-113
+        case ZJ_DE_FORMAT: err_display = e.msg; break;
+        case ZJ_DE_FORMAT_STATIC: err_display = "\"" + e.msg + "\""; break;
+        case ZJ_DE_HUFFMAN_DECODE: err_display = "Error decoding huffman tables.Reason:" + e.msg; break;
+        case ZJ_DE_ZERO_ERROR: err_display = "Image width or height is set to zero, cannot continue"; break;
+        case ZJ_DE_DQT_ERROR: err_display = "Error parsing DQT segment. Reason:" + e.msg; break;
+        case ZJ_DE_SOS_ERROR: err_display = "Error parsing SOS Segment. Reason:" + e.msg; break;
+        case ZJ_DE_SOF_ERROR: err_display = "Error parsing SOF segment. Reason:" + e.msg; break;
+        case ZJ_DE_ILLEGAL_MAGIC_BYTES: err_display = "Error parsing image. Illegal start bytes:" + e.msg; break;
+        case ZJ_DE_MCU_ERROR: err_display = "Error in decoding MCU. Reason " + e.msg; break;
+        case ZJ_DE_EXHAUSTED_DATA: err_display = "Exhausted data in the image"; break;
+        default: err_display = e.msg; break;
+        }
+    }
+    void clear_error() { err_kind = ZJ_DE_NONE; err_msg.clear(); err_display.clear(); }
+};
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+ZJ_API void zj_options_default(zj_options *o)  // ZuneJpegOptions::default, src/options.rs:23-39
+{
+    if (!o) return;
+    o->use_unsafe = 1;
+    o->out_colorspace = ZJ_CS_RGB;
+    o->num_threads = 4;
+    o->max_width = 1 << 14;
+    o->max_height = 1 << 14;
+    o->max_scans = 64;
+    o->strict_mode = 0;
+    o->device = 0;
+}
+
+ZJ_API zj_decoder *zj_decoder_new(const zj_options *o)
+{
+    zj_options opt;
+    if (o) opt = *o; else zj_options_default(&opt);
+    zj_decoder *d = new (std::nothrow) zj_decoder(opt);
+    if (d) d->user_out_cs = opt.out_colorspace;
+    return d;
+}
+ZJ_API void zj_decoder_free(zj_decoder *d) { delete d; }
+
+ZJ_API int zj_decoder_read_headers(zj_decoder *d, const uint8_t *buf, size_t len)
+{
+    if (!d || (!buf && len)) return ZJ_ERR_INVALID_ARG;
+    d->clear_error();
+    try {
+        d->reset_state();
+        Cursor cur{buf, len, 0};
+        d->decode_headers_internal(cur);
+    } catch (DecodeError &e) { d->set_error(e); return ZJ_ERR_DECODE; }
+    return ZJ_OK;
+}
+ZJ_API int zj_decoder_info(const zj_decoder *d, zj_image_info *info)
+{
+    if (!d || !info) return ZJ_ERR_INVALID_ARG;
+    *info = d->info;
+    return ZJ_OK;
+}
+ZJ_API uint32_t zj_decoder_out_colorspace(const zj_decoder *d) { return d ? d->options.out_colorspace : 0; }
+
+ZJ_API int zj_decoder_decode_coefficients(zj_decoder *d, const uint8_t *buf, size_t len, zj_image *img)
+{
+    if (!d || (!buf && len) || !img) return ZJ_ERR_INVALID_ARG;
+    d->clear_error();
+    try { d->host_stage(buf, len, img); } catch (DecodeError &e) { d->set_error(e); return ZJ_ERR_DECODE; }
+    return ZJ_OK;
+}
+
+ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out, size_t *out_len)
+{
+    if (!d || (!buf && len) || !out || !out_len) return ZJ_ERR_INVALID_ARG;
+    *out = nullptr;
+    *out_len = 0;
+    zj_image img;
+    int rc = zj_decoder_decode_coefficients(d, buf, len, &img);
+    if (rc) return rc;
+    const size_t n = zj_output_size(&img);
+    rc = zj_validate_image(&img);
+    if (rc == ZJ_OK && n == 0) rc = ZJ_ERR_INVALID_ARG;
+    uint8_t *o = nullptr;
+    if (rc == ZJ_OK) { o = (uint8_t *)malloc(n ? n : 1); if (!o) rc = ZJ_ERR_OOM; }
+    if (rc == ZJ_OK) rc = zj_gpu_reconstruct(d->options.device, nullptr, &img, 1, &o, &n);
+    if (rc != ZJ_OK) {
+        free(o);
+        std::string m = zj_gpu_strerror(rc);
+        if (rc == ZJ_ERR_CUDA || rc == ZJ_ERR_OOM) m += std::string(" -- ") + zj_gpu_last_cuda_error();
+        d->set_error(DecodeError{rc == ZJ_ERR_UNSUPPORTED ? ZJ_DE_FORMAT : ZJ_DE_GPU, m});
+        return rc;
+    }
+    *out = o;
+    *out_len = n;
+    return ZJ_OK;
+}
+ZJ_API void zj_buffer_free(uint8_t *p) { free(p); }
+ZJ_API int zj_decoder_error_kind(const zj_decoder *d) { return d ? d->err_kind : ZJ_DE_NONE; }
+ZJ_API const char *zj_decoder_error(const zj_decoder *d) { return d ? d->err_display.c_str() : ""; }
+
+}  // extern "C"

@@ -1,0 +1,545 @@
+// zj_kernels.cu -- sm_100a kernels for the post-entropy path of zune-jpeg (reference src/worker.rs:32-251).
+//
+// One fused kernel per (sub-sampling mode, CPU variant mirrored): a CTA owns one TILE of one STRIP and does
+//   phase 1: dequantise + 8x8 integer IDCT + level shift + clamp, one thread per 8x8 block, the whole block in
+//            registers (no transposes: pass A walks rows, pass B walks columns of the same register file);
+//            results go to shared-memory sample planes (u8 for the X86 variant, i16 for SCALAR) together with
+//            the chroma halo blocks the strip-flat up-samplers reach into;
+//   phase 2: chroma up-sampling (the reference's as-written closed forms) +
+//            YCbCr->RGB / YCbCr interleave + the row writer of worker.rs:143-251 (row-tail rule, zero bytes).
+// Bytes the reference never writes are written as zero here, so the output needs no memset.
+//
+// Everything is integer and must be bit-exact against oracle/ (tests/test_gpu_parity.py).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "zj_device.h"
+
+namespace zj {
+
+typedef uint32_t u32;
+
+// ------------------------------------------------------------------------------------------------ IDCT
+// 1-D 8-point kernel: reference src/idct/scalar.rs:79-166 == src/idct/avx2.rs:251-331.  All arithmetic is
+// in Z/2^32 (u32), the final shift is arithmetic.
+template <int SH>
+__device__ __forceinline__ void idct8(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s4, u32 &s5, u32 &s6, u32 &s7, const u32 bias)
+{
+    u32 p1 = (s2 + s6) * 2217u;
+    u32 t2 = p1 + s6 * (u32)(-7567);
+    u32 t3 = p1 + s2 * 3135u;
+    u32 t0 = (s0 + s4) << 12;
+    u32 t1 = (s0 - s4) << 12;
+    u32 x0 = t0 + t3 + bias, x3 = t0 - t3 + bias, x1 = t1 + t2 + bias, x2 = t1 - t2 + bias;
+    u32 a = s7, b = s5, c = s3, d = s1;
+    u32 p3 = a + c, p4 = b + d, q1 = a + d, q2 = b + c;
+    u32 p5 = (p3 + p4) * 4816u;
+    a *= 1223u; b *= 8410u; c *= 12586u; d *= 6149u;
+    q1 = p5 + q1 * (u32)(-3685);
+    q2 = p5 + q2 * (u32)(-10497);
+    p3 *= (u32)(-8034);
+    p4 *= (u32)(-1597);
+    d += q1 + p4; c += q2 + p3; b += q2 + p4; a += q1 + p3;
+    s0 = (u32)((int)(x0 + d) >> SH);
+    s1 = (u32)((int)(x1 + c) >> SH);
+    s2 = (u32)((int)(x2 + b) >> SH);
+    s3 = (u32)((int)(x3 + a) >> SH);
+    s4 = (u32)((int)(x3 - a) >> SH);
+    s5 = (u32)((int)(x2 - b) >> SH);
+    s6 = (u32)((int)(x1 - c) >> SH);
+    s7 = (u32)((int)(x0 - d) >> SH);
+}
+
+__device__ __forceinline__ u32 clamp255(u32 v) { return (u32)max(min((int)v, 255), 0); }
+
+// s16x2 . u8 dot products (IDP.2A): unpack + dequantise one coefficient in a single instruction.
+__device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b) { u32 d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
+__device__ __forceinline__ u32 dp2a_hi(u32 a, u32 b) { u32 d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
+
+__device__ __forceinline__ void store_row(uint8_t *dst, const u32 v[8])
+{
+    uint2 w;
+    w.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    w.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+    *reinterpret_cast<uint2 *>(dst) = w;
+}
+__device__ __forceinline__ void store_row(int16_t *dst, const u32 v[8])
+{
+    uint4 w;
+    w.x = (v[0] & 0xffffu) | (v[1] << 16);
+    w.y = (v[2] & 0xffffu) | (v[3] << 16);
+    w.z = (v[4] & 0xffffu) | (v[5] << 16);
+    w.w = (v[6] & 0xffffu) | (v[7] << 16);
+    *reinterpret_cast<uint4 *>(dst) = w;
+}
+
+// Dequantise + 2-D IDCT + level shift + clamp of one block; rows written to dst[r*dst_stride + 0..7].
+//   VARIANT 0 (X86):    pass A along rows, pass B down columns, DC-only value clamped   (idct/avx2.rs:64-398)
+//   VARIANT 1 (SCALAR): pass A down columns, pass B along rows, DC-only value NOT clamped (idct/scalar.rs:19-282)
+// qtw: 32 words, word k = q[2k] | q[2k+1] << 24 (natural order).  dst rows must be 8 samples-aligned.
+template <int VARIANT, typename ST>
+__device__ __forceinline__ void idct_block(const int16_t *__restrict__ src, const u32 *__restrict__ qtw, ST *__restrict__ dst, int dst_stride)
+{
+    const int4 *p = reinterpret_cast<const int4 *>(src);
+    int4 raw[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) raw[r] = __ldg(p + r);
+
+    u32 acc = ((u32)raw[0].x & 0xffff0000u) | (u32)raw[0].y | (u32)raw[0].z | (u32)raw[0].w;
+#pragma unroll
+    for (int r = 1; r < 8; r++) acc |= (u32)raw[r].x | (u32)raw[r].y | (u32)raw[r].z | (u32)raw[r].w;
+
+    if (acc == 0) {
+        // all 63 AC coefficients zero: ((c0 as i16).wrapping_mul(q0 as i16) >> 3) + 128 in i16
+        // (avx2.rs:159-167 clamps, scalar.rs:45-48 does not)
+        int dc = (int)(int16_t)((u32)raw[0].x & 0xffffu);
+        int q0 = (int)(int16_t)(qtw[0] & 0xffu);
+        int v = (int)(int16_t)(dc * q0);
+        v = (int)(int16_t)((v >> 3) + 128);
+        if (VARIANT == 0) v = max(min(v, 255), 0);
+        u32 vv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) vv[k] = (u32)v;
+#pragma unroll
+        for (int r = 0; r < 8; r++) store_row(dst + r * dst_stride, vv);
+        return;
+    }
+
+    u32 a[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const u32 w[4] = {(u32)raw[r].x, (u32)raw[r].y, (u32)raw[r].z, (u32)raw[r].w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 q = qtw[r * 4 + k];
+            a[r * 8 + 2 * k] = dp2a_lo(w[k], q);
+            a[r * 8 + 2 * k + 1] = dp2a_hi(w[k], q);
+        }
+    }
+    const u32 SCALE_BITS = 512u + 65536u + (128u << 17);
+    if (VARIANT == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            idct8<10>(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7], 512u);
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            idct8<17>(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c], SCALE_BITS);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            idct8<10>(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c], 512u);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            idct8<17>(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7], SCALE_BITS);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        u32 vv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) vv[k] = clamp255(a[r * 8 + k]);
+        store_row(dst + r * dst_stride, vv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- tile geometry
+template <int MODE> struct ModeTraits;
+template <> struct ModeTraits<MODE_NONE> { static constexpr int H = 1, V = 1, YBR = 1, CBR = 1, TM = TM_NONE, HALO = 0; };
+template <> struct ModeTraits<MODE_H>    { static constexpr int H = 2, V = 1, YBR = 2, CBR = 2, TM = TM_H,    HALO = 1; };
+template <> struct ModeTraits<MODE_V>    { static constexpr int H = 1, V = 2, YBR = 2, CBR = 1, TM = TM_V,    HALO = 0; };
+template <> struct ModeTraits<MODE_HV>   { static constexpr int H = 2, V = 2, YBR = 4, CBR = 2, TM = TM_HV,   HALO = 1; };
+
+// Chroma samples of the strip as the reference's up-samplers see them: a FLAT array of CROWS*W samples
+// (row-major).  In shared memory a row holds [left halo block | tile columns | right halo block | special
+// block]; the halo blocks wrap around the image (the flat filters run across row ends).
+template <typename ST>
+struct ChromaView {
+    const ST *base;  // smem plane of one component
+    int W;           // chroma row width in the image
+    int n;           // CROWS * W
+    int c0, c1;      // tile column range [c0, c1)
+    int lhb, rhb, spb;  // block columns held in the left / right / special halo slots (-1 = none)
+    int cs;          // smem row stride (samples)
+    __device__ __forceinline__ int at(int row, int col) const
+    {
+        int lc;
+        if (col >= c0 && col < c1) lc = 8 + (col - c0);
+        else if ((col >> 3) == lhb) lc = col & 7;
+        else if ((col >> 3) == rhb) lc = 8 + (c1 - c0) + (col & 7);
+        else lc = 16 + (c1 - c0) + (col & 7);  // special slot (col >> 3 == spb)
+        return (int)base[row * cs + lc];
+    }
+    __device__ __forceinline__ int flat(int idx) const
+    {
+        int row = idx / W;
+        return at(row, idx - row * W);
+    }
+    // `.get(i).unwrap_or(&0)` of upsampler/avx2.rs:264-270
+    __device__ __forceinline__ int flat_or0(int idx) const { return (idx >= 0 && idx < n) ? flat(idx) : 0; }
+};
+
+__device__ __forceinline__ int T3(int a, int b) { return (3 * a + b + 2) >> 2; }  // (3a + b + 2) >> 2
+
+// ---- H, flat strip of n = 16*W samples, output index o in [0, 2n)        (upsampler/scalar.rs:5-60, sse.rs:24-134)
+template <int VARIANT, typename ST>
+__device__ int up_h(const ChromaView<ST> &v, int o)
+{
+    const int n = v.n;
+    const int i = o >> 1;
+    if (VARIANT == 0 && o >= 2 * n - 8) {  // Q4b: the SSE tail
+        const int il = n - 4;
+        switch (o - (2 * n - 8)) {
+        case 0: return T3(v.flat(il), v.flat(il - 1));
+        case 1: return T3(v.flat(il), v.flat(il + 1));
+        case 2: return T3(v.flat(il + 1), v.flat(il));
+        case 3: return v.flat(il + 1);
+        case 4: return v.flat(il + 2);
+        case 5: return T3(v.flat(il + 2), v.flat(il + 1));
+        case 6: return T3(v.flat(il + 2), v.flat(il + 3));
+        default: return v.flat(il + 3);
+        }
+    }
+    if (o == 0) return v.flat(0);
+    if (o == 1) return T3(v.flat(0), v.flat(1));
+    if (VARIANT == 1) {
+        if (o == 2 * n - 2) return T3(v.flat(n - 2), v.flat(n - 1));  // sic, scalar.rs:55
+        if (o == 2 * n - 1) return v.flat(n - 1);
+    }
+    return (o & 1) ? T3(v.flat(i), v.flat(i + 1)) : T3(v.flat(i), v.flat(i - 1));
+}
+
+// ---- V, 8 rows in, 16 rows out, no neighbour-strip context (upsampler/scalar.rs:64-147, Q4c)
+template <typename ST>
+__device__ int up_v(const ChromaView<ST> &v, int yl, int x)
+{
+    if (yl < 2) return v.at(0, x);
+    if (yl >= 14) return v.at(7, x);
+    const int k = yl >> 1;
+    const int a = v.at(k, x), b = v.at(k + 1, x);
+    return (yl & 1) ? T3(b, a) : T3(a, b);
+}
+
+// ---- HV scalar = H(V(in)) with V seeing 8 double-rows of S = 2W samples (upsampler/scalar.rs:148-166, Q4d)
+template <typename ST>
+__device__ int hv_vo(const ChromaView<ST> &v, int f)
+{
+    const int S = 2 * v.W;
+    const int d = f / S, i = f - d * S, k = d >> 1;
+    if (d < 2) return v.flat(i);
+    if (d >= 14) return v.flat(7 * S + i);
+    const int a = v.flat(k * S + i), b = v.flat((k + 1) * S + i);
+    return (d & 1) ? T3(b, a) : T3(a, b);
+}
+template <typename ST>
+__device__ int up_hv_scalar(const ChromaView<ST> &v, int o)
+{
+    const int n2 = 2 * v.n;  // length of the V output
+    const int i = o >> 1;
+    if (o == 0) return hv_vo(v, 0);
+    if (o == 1) return T3(hv_vo(v, 0), hv_vo(v, 1));
+    if (o == 2 * n2 - 2) return T3(hv_vo(v, n2 - 2), hv_vo(v, n2 - 1));
+    if (o == 2 * n2 - 1) return hv_vo(v, n2 - 1);
+    return (o & 1) ? T3(hv_vo(v, i), hv_vo(v, i + 1)) : T3(hv_vo(v, i), hv_vo(v, i - 1));
+}
+
+// ---- HV AVX2 closed form (upsampler/avx2.rs:29-342)
+template <typename ST>
+__device__ int up_hv_avx(const ChromaView<ST> &v, int o)
+{
+    const int S = v.n >> 3;  // input double-row length = 2W
+    const int L = 2 * S;     // output double-row length
+    const int d2 = o / L;
+    int e = o - d2 * L;
+    const int j = d2 >> 1, far = d2 & 1;
+    const int sj = (j == 0 || j == 7) ? 0 : S;
+    if (far && e == 0) e = 1;  // avx2.rs:330
+    int i = e >> 1;
+    const int odd = e & 1;
+    if (i >= S - 16) {  // last 32 outputs of the double-row: raw input shifted 17 samples left (avx2.rs:277-307,332-338)
+        int k = i - (S - 16);
+        if (k == 15) k = 14;
+        const int c = (j + 1) * S - 33 + k + (far ? sj : 0);
+        return odd ? T3(v.flat(c), v.flat(c + 1)) : T3(v.flat(c), v.flat(c - 1));
+    }
+    const int bj = j * S;
+    auto R = [&](int ii) {
+        const int a = v.flat(bj + ii), b = v.flat(bj + ii + sj);
+        return far ? T3(b, a) : T3(a, b);
+    };
+    const int lane = i & 15, t = i >> 4;
+    int m;
+    if (!odd) {
+        if (lane != 0) m = R(i - 1);
+        else if (t >= 1) { const int p = bj + 16 * t; m = (3 * (v.flat_or0(p) + v.flat_or0(p + sj) + 2)) >> 2; }
+        else if (j == 0) m = v.flat(0);
+        else { const int p = bj - 16, s = (j - 1 == 0) ? 0 : S; m = (3 * (v.flat_or0(p) + v.flat_or0(p + s) + 2)) >> 2; }
+    } else {
+        if (lane != 15) m = R(i + 1);
+        else if (t >= 1) { const int p = bj + 16 * t + 16; m = (3 * (v.flat_or0(p) + v.flat_or0(p + sj) + 2)) >> 2; }
+        else if (j == 0) m = v.flat(16);
+        else { const int p = bj, s = (j - 1 == 0) ? 0 : S; m = (3 * (v.flat_or0(p) + v.flat_or0(p + s) + 2)) >> 2; }
+    }
+    return T3(R(i), m);
+}
+
+// One up-sampled chroma value at strip row yl, luma column x (generic, per-sample path).
+template <int MODE, int VARIANT, typename ST>
+__device__ __forceinline__ int chroma_at(const ChromaView<ST> &v, int yl, int x, int Wp, int hv_avx)
+{
+    if (MODE == MODE_NONE) return v.at(yl, x);
+    if (MODE == MODE_V) return up_v(v, yl, x);
+    const int o = yl * Wp + x;
+    if (MODE == MODE_H) return up_h<VARIANT>(v, o);
+    if (VARIANT == 0 && hv_avx) return up_hv_avx(v, o);
+    return up_hv_scalar(v, o);
+}
+
+// conv16 per pixel: color_convert/scalar.rs:66-85 == avx.rs:123-192 (wrapping i16)
+__device__ __forceinline__ void ycc_to_rgb(int y, int cb, int cr, u32 &r, u32 &g, u32 &b)
+{
+    const int cbb = (int)(int16_t)(cb - 128), crr = (int)(int16_t)(cr - 128);
+    const int rr = (int)(int16_t)(y + ((int)(int16_t)(45 * crr) >> 5));
+    const int gg = (int)(int16_t)(y - ((int)(int16_t)((int)(int16_t)(11 * cbb) + (int)(int16_t)(23 * crr)) >> 5));
+    const int bb = (int)(int16_t)(y + ((int)(int16_t)(113 * cbb) >> 6));
+    r = (u32)max(min(rr, 255), 0);
+    g = (u32)max(min(gg, 255), 0);
+    b = (u32)max(min(bb, 255), 0);
+}
+
+// --------------------------------------------------------------------------------------- the fused kernel
+// grid = (tiles, strips [+1 when rows are dropped], images of this launch group); block = ZJ_THREADS.
+template <int MODE, int VARIANT>
+__global__ void __launch_bounds__(ZJ_THREADS)
+reconstruct_kernel(const DevImage *__restrict__ images)
+{
+    typedef ModeTraits<MODE> MT;
+    typedef typename std::conditional<VARIANT == 0, uint8_t, int16_t>::type ST;
+    constexpr int ROWS = 8 * MT::H * MT::V;   // output rows per strip (mcu.rs:226)
+    constexpr int YROWS = 8 * MT::YBR;        // == ROWS
+    constexpr int CROWS = 8 * MT::CBR;
+    constexpr int TWY = 8 * MT::H * MT::TM;   // luma tile width (samples)
+    constexpr int TWC = 8 * MT::TM;           // chroma tile width
+    constexpr int CS = TWC + 24;              // chroma smem row: halo | tile | halo | special
+    static_assert(YROWS == ROWS, "luma rows");
+
+    __shared__ __align__(16) ST sY[YROWS * TWY];
+    __shared__ __align__(16) ST sC[2][CROWS * CS];
+    __shared__ u32 sQ[3][32];
+
+    const DevImage &im = images[blockIdx.z];
+    const u32 tile = blockIdx.x, strip = blockIdx.y;
+    if (tile >= im.n_tiles) return;
+    const int tid = threadIdx.x;
+    const u32 stride = im.stride;
+    uint8_t *__restrict__ out = im.out;
+
+    // rows below the last processed strip stay zero in the reference (Q1 dropped MCU row, mcu.rs:154,158)
+    if (strip >= im.n_strips) {
+        if (strip > im.n_strips) return;
+        const size_t lo = (size_t)im.n_strips * ROWS * stride, hi = (size_t)im.height * stride;
+        if (lo >= hi) return;
+        const size_t span = hi - lo, per = (span + im.n_tiles - 1) / im.n_tiles;
+        size_t b0 = lo + (size_t)tile * per, b1 = b0 + per;
+        if (b1 > hi) b1 = hi;
+        for (size_t b = b0 + tid; b < b1; b += ZJ_THREADS) out[b] = 0;
+        return;
+    }
+
+    // tile -> MCU column range, spread evenly so that every tile keeps >= TM/2 columns
+    const int mcu_x = (int)im.mcu_x, nt = (int)im.n_tiles;
+    const int m0 = (int)(((long long)tile * mcu_x) / nt), m1 = (int)(((long long)(tile + 1) * mcu_x) / nt);
+    const int tm = m1 - m0;                      // MCU columns in this tile (<= TM)
+    const int Wp = (int)im.Wp, W = (int)im.W;
+    const int ybpr = MT::H * mcu_x;              // luma blocks per block-row of the plane
+
+    for (int k = tid; k < 96; k += ZJ_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 1: IDCT into shared planes
+    const int lhb = (MT::HALO && mcu_x > 0) ? (m0 == 0 ? mcu_x - 1 : m0 - 1) : -1;  // wraps: flat filters cross row ends
+    const int rhb = MT::HALO ? (m1 == mcu_x ? 0 : m1) : -1;
+    // AVX2 HV: lane-0 neighbour of the first vector of a double-row is a stale value taken 16 samples before
+    // the end of the previous double-row (Q4f) -> tile 0 also needs block column mcu_x-2
+    const int spb = (MODE == MODE_HV && VARIANT == 0 && im.hv_avx && m0 == 0 && nt > 1) ? mcu_x - 2 : -1;
+    {
+        const int nY = MT::YBR * MT::H * tm;
+        const int nC = MT::CBR * tm;                  // per chroma component
+        const int nHalo = MT::HALO ? MT::CBR : 0;     // per side per component
+        const int nSp = spb >= 0 ? MT::CBR : 0;
+        const int total = nY + 2 * (nC + 2 * nHalo + nSp);
+        for (int b = tid; b < total; b += ZJ_THREADS) {
+            if (b < nY) {
+                const int br = b / (MT::H * tm), bc = b - br * (MT::H * tm);
+                const size_t blk = ((size_t)strip * MT::YBR + br) * ybpr + (size_t)MT::H * m0 + bc;
+                idct_block<VARIANT, ST>(im.coeff[0] + blk * 64, sQ[0], sY + br * 8 * TWY + bc * 8, TWY);
+            } else {
+                int c = b - nY;
+                const int per = nC + 2 * nHalo + nSp;
+                const int comp = c / per;
+                c -= comp * per;
+                int br, gcol, lcol;  // block row, global block column, smem column
+                if (c < nC) { br = c / tm; const int bc = c - br * tm; gcol = m0 + bc; lcol = 8 + bc * 8; }
+                else if (c < nC + nHalo) { br = c - nC; gcol = lhb; lcol = 0; }
+                else if (c < nC + 2 * nHalo) { br = c - nC - nHalo; gcol = rhb; lcol = 8 + tm * 8; }
+                else { br = c - nC - 2 * nHalo; gcol = spb; lcol = 16 + tm * 8; }
+                const size_t blk = ((size_t)strip * MT::CBR + br) * mcu_x + gcol;
+                idct_block<VARIANT, ST>(im.coeff[1 + comp] + blk * 64, sQ[1 + comp], sC[comp] + br * 8 * CS + lcol, CS);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 2: up-sample, convert, write
+    ChromaView<ST> cv[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        cv[c].base = sC[c]; cv[c].W = W; cv[c].n = CROWS * W;
+        cv[c].c0 = m0 * 8; cv[c].c1 = m1 * 8; cv[c].lhb = lhb; cv[c].rhb = rhb; cv[c].spb = spb; cv[c].cs = CS;
+    }
+    const int X0 = m0 * 8 * MT::H;           // first luma column of the tile
+    const int tw = tm * 8 * MT::H;           // luma columns in the tile
+    const bool last_tile = (tile + 1 == (u32)nt);
+    const u32 y_base = strip * ROWS;
+    const u32 n_norm = im.n_norm, T = im.T, P = im.P;
+    const bool ycc = im.out_kind == OUT_YCC;
+    const int hv_avx = (int)im.hv_avx;
+
+    if (im.small_width) {
+        // width < 16: the first 16 samples (zero-padded past Wp) are converted into a 16*nc-byte temp and its
+        // first width*nc bytes are copied out (worker.rs:176-198).  A single tile covers the row.
+        const u32 rowbytes = im.width * im.nc;
+        for (int u = tid; u < ROWS * 16; u += ZJ_THREADS) {
+            const int yl = u >> 4, s = u & 15;
+            const u32 y = y_base + yl;
+            if (y >= im.height) continue;
+            int yy = 0, cb = 0, cr = 0;
+            if (s < Wp) {
+                yy = (int)sY[yl * TWY + s];
+                cb = chroma_at<MODE, VARIANT, ST>(cv[0], yl, s, Wp, hv_avx);
+                cr = chroma_at<MODE, VARIANT, ST>(cv[1], yl, s, Wp, hv_avx);
+            }
+            u32 px[3];
+            ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
+            uint8_t *row = out + (size_t)y * stride;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const u32 b = 3 * s + c; if (b < rowbytes) row[b] = (uint8_t)px[c]; }
+            if (s == 0) for (u32 b = 48; b < rowbytes; b++) row[b] = 0;
+        }
+        return;
+    }
+
+    for (int u = tid; u < ROWS * (tw >> 3); u += ZJ_THREADS) {
+        const int yl = u / (tw >> 3);
+        const int xl = (u - yl * (tw >> 3)) << 3;  // tile-local luma column of this 8-sample unit
+        const u32 y = y_base + yl;
+        if (y >= im.height) continue;              // rows past the image are truncated (mcu.rs:375)
+        uint8_t *row = out + (size_t)y * stride;
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+            const int s = X0 + xl + k;             // sample (luma column) in the padded row
+            const bool normal = (u32)s < n_norm;
+            const bool tail = (T != 0xffffffffu) && s >= Wp - 16;
+            if (!normal && !tail) continue;
+            const int yy = (int)sY[yl * TWY + xl + k];
+            const int cb = chroma_at<MODE, VARIANT, ST>(cv[0], yl, s, Wp, hv_avx);
+            const int cr = chroma_at<MODE, VARIANT, ST>(cv[1], yl, s, Wp, hv_avx);
+            u32 px[3];
+            if (ycc) { px[0] = (u32)yy & 0xff; px[1] = (u32)cb & 0xff; px[2] = (u32)cr & 0xff; }  // `as u8`
+            else ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
+            if (normal) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { const u32 b = 3 * s + c; if (!(b >= T && b < T + 48)) row[b] = (uint8_t)px[c]; }
+            }
+            if (tail) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) row[T + 3 * (s - (Wp - 16)) + c] = (uint8_t)px[c];
+            }
+        }
+    }
+    // bytes of the row nobody writes: [P, stride) minus the tail chunk (Q5: 16 zero bytes; Q6: the w "alpha" bytes)
+    if (last_tile) {
+        const u32 nz = stride > P ? stride - P : 0;
+        for (u32 u = tid; u < (u32)ROWS * nz; u += ZJ_THREADS) {
+            const u32 yl = u / nz, b = P + (u - yl * nz);
+            const u32 y = y_base + yl;
+            if (y < im.height && !(b >= T && b < T + 48)) out[(size_t)y * stride + b] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- luma-only kernel
+// (YCbCr | GRAYSCALE) -> GRAYSCALE: IDCT of the Y plane only (worker.rs:59,115-118), `as u8` row copy
+// (color_convert/scalar.rs:91-114; Q7 is resolved on the host: geometries where the reference panics are
+// rejected before launch).  grid = (ceil(blocks per block-row / 128), block-rows + 1, images).
+template <int VARIANT>
+__global__ void __launch_bounds__(ZJ_THREADS)
+gray_kernel(const DevImage *__restrict__ images, int rows_per_strip)
+{
+    typedef typename std::conditional<VARIANT == 0, uint8_t, int16_t>::type ST;
+    __shared__ __align__(16) ST sT[ZJ_THREADS][64 + 8];  // one block per thread, padded
+    __shared__ u32 sQ[32];
+    const DevImage &im = images[blockIdx.z];
+    const int tid = threadIdx.x;
+    const int ybpr = (int)(im.Wp >> 3);
+    const u32 brows = im.n_strips * (u32)(rows_per_strip >> 3);  // block rows the reference processes
+    const u32 br = blockIdx.y;
+    uint8_t *__restrict__ out = im.out;
+    if (br >= brows) {
+        if (br > brows) return;
+        const size_t lo = (size_t)brows * 8 * im.stride, hi = (size_t)im.height * im.stride;
+        if (lo >= hi) return;
+        const size_t span = hi - lo, per = (span + gridDim.x - 1) / gridDim.x;
+        size_t b0 = lo + (size_t)blockIdx.x * per, b1 = b0 + per;
+        if (b1 > hi) b1 = hi;
+        for (size_t b = b0 + tid; b < b1; b += ZJ_THREADS) out[b] = 0;
+        return;
+    }
+    if (tid < 32) sQ[tid] = im.qtw[0][tid];
+    __syncthreads();
+    const int bc = blockIdx.x * ZJ_THREADS + tid;
+    if (bc >= ybpr) return;
+    const size_t blk = (size_t)br * ybpr + bc;
+    idct_block<VARIANT, ST>(im.coeff[0] + blk * 64, sQ, &sT[tid][0], 8);
+    const u32 x0 = (u32)bc * 8;
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        const u32 y = br * 8 + r;
+        if (y >= im.height) break;
+        uint8_t *row = out + (size_t)y * im.stride;
+        for (int k = 0; k < 8; k++)
+            if (x0 + k < im.width) row[x0 + k] = (uint8_t)((u32)sT[tid][r * 8 + k] & 0xff);
+    }
+}
+
+// ----------------------------------------------------------------------------------------- host launchers
+template <int MODE, int VARIANT>
+static cudaError_t launch_reconstruct(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
+{
+    dim3 grid(g.max_tiles, g.max_strips + 1, g.count);
+    reconstruct_kernel<MODE, VARIANT><<<grid, ZJ_THREADS, 0, stream>>>(d_images + g.first);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_group(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
+{
+    if (g.gray) {
+        const int rows = g.mode == MODE_NONE ? 8 : (g.mode == MODE_HV ? 32 : 16);
+        dim3 grid(g.max_tiles, g.max_strips * (rows >> 3) + 1, g.count);
+        if (g.variant == 0) gray_kernel<0><<<grid, ZJ_THREADS, 0, stream>>>(d_images + g.first, rows);
+        else gray_kernel<1><<<grid, ZJ_THREADS, 0, stream>>>(d_images + g.first, rows);
+        return cudaGetLastError();
+    }
+    switch (g.mode * 2 + g.variant) {
+    case MODE_NONE * 2 + 0: return launch_reconstruct<MODE_NONE, 0>(d_images, g, stream);
+    case MODE_NONE * 2 + 1: return launch_reconstruct<MODE_NONE, 1>(d_images, g, stream);
+    case MODE_H * 2 + 0: return launch_reconstruct<MODE_H, 0>(d_images, g, stream);
+    case MODE_H * 2 + 1: return launch_reconstruct<MODE_H, 1>(d_images, g, stream);
+    case MODE_V * 2 + 0: return launch_reconstruct<MODE_V, 0>(d_images, g, stream);
+    case MODE_V * 2 + 1: return launch_reconstruct<MODE_V, 1>(d_images, g, stream);
+    case MODE_HV * 2 + 0: return launch_reconstruct<MODE_HV, 0>(d_images, g, stream);
+    default: return launch_reconstruct<MODE_HV, 1>(d_images, g, stream);
+    }
+}
+
+}  // namespace zj
