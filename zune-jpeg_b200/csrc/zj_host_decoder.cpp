@@ -8,12 +8,14 @@
 // what happens after a marker is met inside a scan), same restart bookkeeping, same errors.
 // The branchy bit-serial work stays on the CPU by design; everything after it runs in zj_kernels.cu.
 #include <cuda_runtime.h>
+#include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <string>
 #include <vector>
 
