@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pixel-reconstruction path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3_444|c3_gray|c4|c5]
+
+A "step" is one pass of the hot path (dequant + IDCT + upsample + YCbCr->RGB, reference src/worker.rs:32)
+over one batch of synthetic images.  Default workload = BASELINE.json configs[1]: a batch of 256 synthetic
+3840x2160 baseline 4:2:0 JPEGs -> RGB on one B200.  The JPEGs are generated in-bench (seeded smooth random
+images, quality 90), entropy-decoded by the host front-end into i16 coefficient planes, and then
+
+  value  : whole-job MP/s with the planes ALREADY RESIDENT in HBM (CUDA events on the launching stream)
+  e2e    : the same metric through the C-ABI call a host program makes (zj_gpu_reconstruct) with PINNED HOST
+           buffers: H2D of every plane and D2H of every pixel inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+
+`--impl reference` times the reference's CPU implementation of the same path on the host cores.  The reference
+is Rust and cannot be built in this environment, so that arm runs the oracle port (oracle/, X86 variant = what
+`use_unsafe=true` executes on an AVX2 host) with all host threads, strip-parallel like scoped_threadpool.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: (width, height, subsampling, progressive, gray, out_cs, default batch, description)
+    "c2": (3840, 2160, "420", False, False, 0, 256, "3840x2160 baseline 4:2:0 JPEG batch of 256 -> RGB (BASELINE configs[1])"),
+    "c3_444": (4096, 4096, "444", False, False, 0, 32, "4096x4096 baseline 4:4:4 JPEG batch -> RGB (BASELINE configs[2])"),
+    "c3_gray": (4096, 4096, "444", False, True, 1, 64, "4096x4096 grayscale JPEG batch -> gray (BASELINE configs[2])"),
+    "c4": (1920, 1080, "422", True, False, 0, 256, "1920x1080 progressive 4:2:2 JPEG batch -> RGB (BASELINE configs[3])"),
+    "c5": (8192, 8192, "420", False, False, 5, 16, "8192x8192 baseline 4:2:0 + restart markers batch -> RGBA (BASELINE configs[4])"),
+}
+B_PER_PX = {"c2": 6, "c3_444": 9, "c3_gray": 3, "c4": 7, "c5": 7}  # 2 B x samples/px + out B/px
+
+
+def metric_name() -> str:
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "decoded MP/s (dequant+IDCT+upsample+YCbCr→RGB), 4K 4:2:0 batch @1/2/4/8 B200"
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_pool(cfg: str, n_distinct: int, rank: int):
+    """n_distinct synthetic JPEGs -> host stage -> (descriptor, planes) per image."""
+    import jpeg_util
+    from zune_jpeg_b200.decoder import ColorSpace, Decoder, ZuneJpegOptions
+    w, h, sub, prog, gray, out_cs, _, _ = CONFIGS[cfg]
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        data = jpeg_util.synth_jpeg(1000 * rank + i, w, h, sub, 90, prog, gray, restart_rows=1 if cfg == "c5" else 0)
+        d = Decoder.new_with_options(ZuneJpegOptions().set_out_colorspace(ColorSpace(out_cs)))
+        img, planes = d.decode_coefficients(data)
+        return img, planes, len(data)
+
+    with ThreadPoolExecutor(max_workers=min(n_distinct, host_threads())) as ex:
+        return list(ex.map(one, range(n_distinct)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = [float(r[1]) for r in rows if len(r) >= 8]
+            if sm:
+                out["sm_mhz"] = statistics.median(sm)
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 8)
+                out["samples"] = len(sm)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                out["reasons"] = [n for k, n in enumerate(names) if any(r[4 + k].strip() == "Active" for r in rows if len(r) >= 8)]
+        except Exception:
+            pass
+        return out
+
+
+def time_cpu_port(pool, seconds: float, threads: int):
+    """oracle (X86 variant) strip-parallel on `threads` host threads; returns (MP/s, n images timed)."""
+    import oracle
+    imgs = []
+    for (img, planes, _) in pool:
+        for z in range(img.n_comp):
+            img.comp[z].coeff = planes[z].ctypes.data
+        imgs.append(img)
+    mp = sum(i.width * i.height for i in imgs) / 1e6
+    oracle.reconstruct(imgs[0], threads=threads)  # warm-up (page in, thread start)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        for im in imgs:
+            oracle.reconstruct(im, threads=threads)
+        n += len(imgs)
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return mp * (n / len(imgs)) / dt, n
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path on all host threads (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = args.config
+    w, h = CONFIGS[cfg][0], CONFIGS[cfg][1]
+    threads = host_threads()
+    n_sample = 8 if w * h <= 3840 * 2160 else 2
+    pool = make_pool(cfg, n_sample, 0)
+    import oracle
+    imgs = []
+    for (img, planes, _) in pool:
+        for z in range(img.n_comp):
+            img.comp[z].coeff = planes[z].ctypes.data
+        imgs.append(img)
+    mp_step = sum(i.width * i.height for i in imgs) / 1e6
+
+    def step():
+        for im in imgs:
+            oracle.reconstruct(im, threads=threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = mp_step * args.steps / dt
+    sample = f"{n_sample} of the workload's images per step ({n_sample}x {w}x{h}), coefficient planes in RAM -> pixels in RAM"
+    line = {
+        "impl": "reference", "metric": metric_name(), "value": round(value, 2), "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": CONFIGS[cfg][7], "sample": sample, "threads": threads,
+                   "note": "reference is Rust (no rustc/cargo here): this is the C oracle port of the same path, real AVX2/SSE4.1 intrinsics, strip-parallel"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    from zune_jpeg_b200 import gpu
+    from zune_jpeg_b200._ffi import ZjImage
+    from zune_jpeg_b200.sharding import Plumbing
+    import ctypes as C
+
+    pl = Plumbing()  # torch.distributed only when WORLD_SIZE > 1
+    rank, device, world = pl.rank, pl.local_rank, pl.world
+    if gpu.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    cfg = args.config
+    w, h, sub, prog, gray, out_cs, def_batch, desc = CONFIGS[cfg]
+    batch = args.batch or def_batch
+    n_distinct = min(args.distinct, batch)
+    t_setup = time.perf_counter()
+    pool = make_pool(cfg, n_distinct, rank)
+
+    # ---- device-resident batch: every batch entry owns its planes and its output in HBM
+    stream = gpu.Stream(device)
+    plane_bytes = [sum(p.nbytes for p in planes) for (_, planes, _) in pool]
+    out_bytes = gpu.output_size(pool[0][0])
+    dev_planes, dev_out, images = [], [], []
+    for b in range(batch):
+        img, planes, _ = pool[b % n_distinct]
+        bufs = []
+        for p in planes:
+            if p.nbytes:
+                d = gpu.DeviceBuffer(p.nbytes, device)
+                d.upload(p, stream.ptr)
+                bufs.append(d)
+            else:
+                bufs.append(None)
+        dev_planes.append(bufs)
+        o = gpu.DeviceBuffer(out_bytes, device)
+        dev_out.append(o)
+        di = ZjImage()
+        C.memmove(C.byref(di), C.byref(img), C.sizeof(ZjImage))
+        for z in range(img.n_comp):
+            di.comp[z].coeff = bufs[z].ptr if bufs[z] is not None else None
+        images.append(di)
+    stream.synchronize()
+    plan = gpu.Batch(images, [o.ptr for o in dev_out], [out_bytes] * batch, device)
+    algo_bytes = plan.algorithmic_bytes
+    mp_step = batch * w * h / 1e6
+
+    # correctness spot check inside the bench: first image against the oracle (the checker, not the product)
+    check = None
+    if not args.no_check:
+        import oracle
+        plan.run(stream.ptr)
+        stream.synchronize()
+        got = dev_out[0].download(stream=stream.ptr)
+        img0, planes0, _ = pool[0]
+        for z in range(img0.n_comp):
+            img0.comp[z].coeff = planes0[z].ctypes.data
+        want = oracle.reconstruct(img0, threads=host_threads())
+        check = bool(np.array_equal(got, want))
+        if not check:
+            raise SystemExit("bench.py: GPU output differs from the oracle -- refusing to report a number")
+
+    # ---- timed region: W warm-up steps, then exactly K steps between barriers, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        plan.run(stream.ptr)
+    stream.synchronize()
+    pl.barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
+    ev0, ev1 = gpu.Event(device), gpu.Event(device)
+    launches0 = gpu.launch_count()
+    ev0.record(stream.ptr)
+    for _ in range(args.steps):
+        plan.run(stream.ptr)
+    ev1.record(stream.ptr)
+    stream.synchronize()
+    pl.barrier()
+    ms = ev0.elapsed_ms(ev1)
+    launches = gpu.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_max = pl.max(ms)
+    total_mp = pl.sum(mp_step * args.steps)
+    value = total_mp / (ms_max / 1e3)
+
+    # ---- e2e: zj_gpu_reconstruct with pinned HOST planes and pinned HOST outputs (H2D + kernels + D2H timed)
+    e2e = None
+    if not args.no_e2e:
+        pinned_planes = []
+        for (img, planes, _) in pool:
+            row = []
+            for p in planes:
+                if p.nbytes:
+                    pb = gpu.PinnedBuffer(p.nbytes)
+                    pb.array[:] = p.view(np.uint8)
+                    row.append(pb)
+                else:
+                    row.append(None)
+            pinned_planes.append(row)
+        pinned_out = gpu.PinnedBuffer(out_bytes * batch)
+        himgs = (ZjImage * batch)()
+        optrs = (C.c_void_p * batch)()
+        olens = (C.c_size_t * batch)()
+        for b in range(batch):
+            img = pool[b % n_distinct][0]
+            C.memmove(C.byref(himgs[b]), C.byref(img), C.sizeof(ZjImage))
+            for z in range(img.n_comp):
+                pb = pinned_planes[b % n_distinct][z]
+                himgs[b].comp[z].coeff = pb.ptr if pb is not None else None
+            optrs[b] = pinned_out.ptr + b * out_bytes
+            olens[b] = out_bytes
+        from zune_jpeg_b200 import _ffi
+        lib = _ffi.load()
+        k_e2e = max(1, min(args.steps, args.e2e_steps))
+
+        def e2e_step():
+            rc = lib.zj_gpu_reconstruct(device, stream.ptr, himgs, batch, optrs, olens)
+            if rc != 0:
+                raise SystemExit(f"zj_gpu_reconstruct failed: {rc} {lib.zj_gpu_last_cuda_error().decode()}")
+
+        e2e_step()  # warm-up (stream-ordered allocator pools, page faults)
+        pl.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        stream.synchronize()
+        dt = time.perf_counter() - t0
+        pl.barrier()
+        dt_max = pl.max(dt)
+        e2e_value = pl.sum(mp_step * k_e2e) / dt_max
+        h2d = sum(plane_bytes[b % n_distinct] for b in range(batch))
+        e2e = {"value": round(e2e_value, 2), "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_bytes * batch),
+               "steps": k_e2e, "ms_per_step": round(1e3 * dt_max / k_e2e, 3),
+               "how": "zj_gpu_reconstruct (C ABI), pinned host coefficient planes in, pinned host pixels out, wall clock around the synchronous call"}
+        if not args.no_check:
+            first = np.ctypeslib.as_array((C.c_uint8 * out_bytes).from_address(pinned_out.ptr))
+            if not np.array_equal(first, want):
+                raise SystemExit("bench.py: e2e output differs from the oracle")
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_threads()
+        v, n = time_cpu_port(pool, args.cpu_seconds, threads)
+        cpu = {"value": round(v, 2), "unit": "MP/s", "cores": threads, "kind": "port",
+               "sample": f"{n} images ({n_distinct} distinct {w}x{h}, repeated for >= {args.cpu_seconds:.0f} s), planes in RAM -> pixels in RAM, oracle X86 variant, strip-parallel"}
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kernel_ms = ms / max(launches, 1)
+    achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(kernel_ms, 4),
+                "kernel": "zj::reconstruct_kernel (one launch per step covers the whole batch)"}
+
+    if rank == 0:
+        line = {
+            "metric": metric_name(), "value": round(value, 2), "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": batch, "distinct_images": n_distinct, "jpeg_quality": 90,
+                       "variant": "X86 (use_unsafe=true)", "bytes_per_px": B_PER_PX[cfg],
+                       "l2": f"inputs {algo_bytes / 1e9:.2f} GB per step per GPU, far larger than the 126 MB L2 (no flush needed)",
+                       "parallelism": f"images sharded over {world} GPU(s), no collective"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "checked_vs_oracle": check, "setup_s": round(time.perf_counter() - t_setup, 1),
+        }
+        print(json.dumps(line))
+    pl.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic JPEGs cycled through the batch")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    import __graft_entry__
+    if not os.path.exists(__graft_entry__.LIB):
+        __graft_entry__.build()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -307,6 +307,164 @@ __device__ __forceinline__ void ycc_to_rgb(int y, int cb, int cr, u32 &r, u32 &g
     b = (u32)max(min(bb, 255), 0);
 }
 
+
+// ------------------------------------------------------------------------- generic (edge) path, out of line
+// Every quirk of the reference, any variant, one sample at a time.  Kept __noinline__ so that the hot loop of
+// the kernel stays small enough for the instruction cache; only edge units of a tile come here.
+template <typename ST>
+struct SlowCtx {
+    ChromaView<ST> cv[2];
+    const ST *sY;
+    uint8_t *out;
+    int twy, X0, Wp, hv_avx;
+    u32 y_base, height, stride, n_norm, T, width, nc;
+    bool ycc;
+};
+
+template <int MODE, int VARIANT, typename ST>
+__device__ __noinline__ void slow_row8(const SlowCtx<ST> &c, int yl, int xl)
+{
+    const u32 y = c.y_base + yl;
+    if (y >= c.height) return;                 // rows past the image are truncated (mcu.rs:375)
+    uint8_t *row = c.out + (size_t)y * c.stride;
+    const u32 T = c.T;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        const int s = c.X0 + xl + k;           // sample (luma column) in the padded row
+        const bool normal = (u32)s < c.n_norm;
+        const bool tail = (T != 0xffffffffu) && s >= c.Wp - 16;
+        if (!normal && !tail) continue;
+        const int yy = (int)c.sY[yl * c.twy + xl + k];
+        const int cb = chroma_at<MODE, VARIANT, ST>(c.cv[0], yl, s, c.Wp, c.hv_avx);
+        const int cr = chroma_at<MODE, VARIANT, ST>(c.cv[1], yl, s, c.Wp, c.hv_avx);
+        u32 px[3];
+        if (c.ycc) { px[0] = (u32)yy & 0xff; px[1] = (u32)cb & 0xff; px[2] = (u32)cr & 0xff; }  // `as u8`
+        else ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
+        if (normal) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) { const u32 b = 3 * s + ch; if (!(b >= T && b < T + 48)) row[b] = (uint8_t)px[ch]; }
+        }
+        if (tail) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) row[T + 3 * (s - (c.Wp - 16)) + ch] = (uint8_t)px[ch];
+        }
+    }
+}
+
+// width < 16: the first 16 samples (zero-padded past Wp) are converted into a 16*nc-byte temp and its first
+// width*nc bytes are copied out (worker.rs:176-198).  A single tile covers the row.
+template <int MODE, int VARIANT, typename ST>
+__device__ __noinline__ void slow_small_width(const SlowCtx<ST> &c, int rows, int tid)
+{
+    const u32 rowbytes = c.width * c.nc;
+    for (int u = tid; u < rows * 16; u += ZJ_THREADS) {
+        const int yl = u >> 4, s = u & 15;
+        const u32 y = c.y_base + yl;
+        if (y >= c.height) continue;
+        int yy = 0, cb = 0, cr = 0;
+        if (s < c.Wp) {
+            yy = (int)c.sY[yl * c.twy + s];
+            cb = chroma_at<MODE, VARIANT, ST>(c.cv[0], yl, s, c.Wp, c.hv_avx);
+            cr = chroma_at<MODE, VARIANT, ST>(c.cv[1], yl, s, c.Wp, c.hv_avx);
+        }
+        u32 px[3];
+        ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
+        uint8_t *row = c.out + (size_t)y * c.stride;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) { const u32 b = 3 * s + ch; if (b < rowbytes) row[b] = (uint8_t)px[ch]; }
+        if (s == 0) for (u32 b = 48; b < rowbytes; b++) row[b] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------ packed fast path
+// Interior units (everything but the image / strip / AVX2-vector edge cases listed at the call site) are
+// computed 8 pixels at a time on 16x2 lane pairs: VIADD.16x2 / VIMNMX.S16x2.RELU clamp two lanes per
+// instruction, IDP.2A evaluates 3a+b+2 of the triangle filter in one instruction, PRMT does all byte traffic.
+// Only for the X86 variant (its samples are clamped to [0,255] and live as bytes in shared memory).
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 s) { return __byte_perm(a, b, s); }
+__device__ __forceinline__ u32 lanes01(u32 w) { return prmt(w, 0u, 0x4140u); }  // bytes 0,1 -> 16-bit lanes
+__device__ __forceinline__ u32 lanes23(u32 w) { return prmt(w, 0u, 0x4342u); }  // bytes 2,3 -> 16-bit lanes
+__device__ __forceinline__ u32 vadd2(u32 a, u32 b) { u32 d; asm("add.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ u32 maxu2(u32 a, u32 b) { u32 d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ u32 minu2(u32 a, u32 b) { u32 d; asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ u32 minrelu2(u32 a, u32 b) { u32 d; asm("min.relu.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ u32 dp2a_u(u32 a, u32 b, u32 c) { u32 d; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// T(a,b) = (3a + b + 2) >> 2 on both lanes (values <= 255, so no lane overflows)
+__device__ __forceinline__ u32 T2(u32 a, u32 b) { return ((a * 3u + b + 0x00020002u) >> 2) & 0x00ff00ffu; }
+
+// Horizontal x2 triangle filter of four samples R0..R3 with neighbours R(-1), R4:
+//   out[2i] = T(R[i], R[i-1]), out[2i+1] = T(R[i], R[i+1])    (upsampler/scalar.rs:30-42 == avx2.rs:178-197)
+// h = (R(-1), R4), a = (R0, R1), b = (R2, R3) as lane pairs; o[k] = (out[2k], out[2k+1]) as lane pairs.
+__device__ __forceinline__ void hfilter8(u32 h, u32 a, u32 b, u32 o[4])
+{
+    const u32 W13 = 0x0301u, W31 = 0x0103u;                                  // lane0*1 + lane1*3 / lane0*3 + lane1*1
+    const u32 qm1 = prmt(h, a, 0x5410u);                                      // (R(-1), R0)
+    const u32 q1 = prmt(a, b, 0x5432u);                                       // (R1, R2)
+    const u32 q3 = prmt(b, h, 0x7632u);                                       // (R3, R4)
+    const u32 o0 = dp2a_u(qm1, W13, 2u), o1 = dp2a_u(a, W31, 2u), o2 = dp2a_u(a, W13, 2u), o3 = dp2a_u(q1, W31, 2u);
+    const u32 o4 = dp2a_u(q1, W13, 2u), o5 = dp2a_u(b, W31, 2u), o6 = dp2a_u(b, W13, 2u), o7 = dp2a_u(q3, W31, 2u);
+    // pack two results into lanes, shift both at once, mask off the bits that crossed the lane boundary
+    // (results reach 287 when a mis-scaled lane-0/15 neighbour is involved, hence 9-bit lanes)
+    o[0] = ((o0 + (o1 << 16)) >> 2) & 0x01ff01ffu;
+    o[1] = ((o2 + (o3 << 16)) >> 2) & 0x01ff01ffu;
+    o[2] = ((o4 + (o5 << 16)) >> 2) & 0x01ff01ffu;
+    o[3] = ((o6 + (o7 << 16)) >> 2) & 0x01ff01ffu;
+}
+
+// conv16 on lane pairs (color_convert/avx.rs:123-192), exact for y in [0,255], cb/cr in [0,287]:
+//   r = clamp(y + ((45*(cr-128)) >> 5))           = clamp((32y + 45cr - 5760) >> 5)
+//   g = clamp(y - ((11*(cb-128)+23*(cr-128)) >> 5)) = clamp((32y - 11cb - 23cr + 4352 + 31) >> 5)   [-floor(t/32) = floor((31-t)/32)]
+//   b = clamp(y + ((113*(cb-128)) >> 6))          = clamp((64y + 113cb - 14464) >> 6)
+// clamping before the shift (to 255*32+31 / 255*64+63) equals clamping after it.  Results: bytes 0 and 2.
+__device__ __forceinline__ void convert_pair(u32 y, u32 cb, u32 cr, u32 &r, u32 &g, u32 &b)
+{
+    const u32 y32 = y << 5;
+    r = minrelu2(vadd2(cr * 45u + y32, 0xE980E980u), 0x1FFF1FFFu) >> 5;                          // -5760
+    g = minrelu2(vadd2(y32 + 0x331F331Fu - cb * 11u - cr * 23u, 0xDE00DE00u), 0x1FFF1FFFu) >> 5;  // +13087, then -8704
+    // 64y + 113cb reaches 48751 (> i16 range), so this channel is clamped as unsigned lanes: [14464, 30847] - 14464
+    b = (minu2(maxu2(cb * 113u + (y32 << 1), 0x38803880u), 0x787F787Fu) - 0x38803880u) >> 6;
+}
+
+// 8 pixels -> 24 interleaved bytes.  c0/c1/c2 hold channel pairs with the values in bytes 0 and 2.
+__device__ __forceinline__ void pack24(const u32 c0[4], const u32 c1[4], const u32 c2[4], u32 w[6])
+{
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const u32 rg0 = prmt(c0[2 * h], c1[2 * h], 0x6240u);          // [R0 G0 R1 G1]
+        const u32 rg1 = prmt(c0[2 * h + 1], c1[2 * h + 1], 0x6240u);  // [R2 G2 R3 G3]
+        w[3 * h] = prmt(rg0, c2[2 * h], 0x2410u);                      // [R0 G0 B0 R1]
+        w[3 * h + 1] = prmt(prmt(rg0, c2[2 * h], 0x0063u), rg1, 0x5410u);  // [G1 B1 R2 G2]
+        w[3 * h + 2] = prmt(rg1, c2[2 * h + 1], 0x6324u);              // [B2 R3 G3 B3]
+    }
+}
+
+__device__ __forceinline__ void emit8(uint8_t *dst, const u32 y[4], const u32 cb[4], const u32 cr[4], bool ycc, bool align8)
+{
+    u32 w[6];
+    if (ycc) {
+        pack24(y, cb, cr, w);  // `as u8` interleave (color_convert/scalar.rs:152-161)
+    } else {
+        u32 r[4], g[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) convert_pair(y[k], cb[k], cr[k], r[k], g[k], b[k]);
+        pack24(r, g, b, w);
+    }
+    if (align8) {
+        uint2 *d = reinterpret_cast<uint2 *>(dst);
+        d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
+    } else {
+        u32 *d = reinterpret_cast<u32 *>(dst);
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = w[k];
+    }
+}
+
+__device__ __forceinline__ void load_y8(const uint8_t *p, u32 y[4])
+{
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    y[0] = lanes01(v.x); y[1] = lanes23(v.x); y[2] = lanes01(v.y); y[3] = lanes23(v.y);
+}
+
 // --------------------------------------------------------------------------------------- the fused kernel
 // grid = (tiles, strips [+1 when rows are dropped], images of this launch group); block = ZJ_THREADS.
 template <int MODE, int VARIANT>
@@ -369,10 +527,14 @@ reconstruct_kernel(const DevImage *__restrict__ images)
         const int nSp = spb >= 0 ? MT::CBR : 0;
         const int total = nY + 2 * (nC + 2 * nHalo + nSp);
         for (int b = tid; b < total; b += ZJ_THREADS) {
+            const int16_t *src;
+            const u32 *qt;
+            ST *dst;
+            int dstride;
             if (b < nY) {
                 const int br = b / (MT::H * tm), bc = b - br * (MT::H * tm);
                 const size_t blk = ((size_t)strip * MT::YBR + br) * ybpr + (size_t)MT::H * m0 + bc;
-                idct_block<VARIANT, ST>(im.coeff[0] + blk * 64, sQ[0], sY + br * 8 * TWY + bc * 8, TWY);
+                src = im.coeff[0] + blk * 64; qt = sQ[0]; dst = sY + br * 8 * TWY + bc * 8; dstride = TWY;
             } else {
                 int c = b - nY;
                 const int per = nC + 2 * nHalo + nSp;
@@ -384,18 +546,19 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                 else if (c < nC + 2 * nHalo) { br = c - nC - nHalo; gcol = rhb; lcol = 8 + tm * 8; }
                 else { br = c - nC - 2 * nHalo; gcol = spb; lcol = 16 + tm * 8; }
                 const size_t blk = ((size_t)strip * MT::CBR + br) * mcu_x + gcol;
-                idct_block<VARIANT, ST>(im.coeff[1 + comp] + blk * 64, sQ[1 + comp], sC[comp] + br * 8 * CS + lcol, CS);
+                src = im.coeff[1 + comp] + blk * 64; qt = sQ[1 + comp]; dst = sC[comp] + br * 8 * CS + lcol; dstride = CS;
             }
+            idct_block<VARIANT, ST>(src, qt, dst, dstride);  // the only call site: one copy of the unrolled IDCT
         }
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 2: up-sample, convert, write
-    ChromaView<ST> cv[2];
+    SlowCtx<ST> sc;
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-        cv[c].base = sC[c]; cv[c].W = W; cv[c].n = CROWS * W;
-        cv[c].c0 = m0 * 8; cv[c].c1 = m1 * 8; cv[c].lhb = lhb; cv[c].rhb = rhb; cv[c].spb = spb; cv[c].cs = CS;
+        sc.cv[c].base = sC[c]; sc.cv[c].W = W; sc.cv[c].n = CROWS * W;
+        sc.cv[c].c0 = m0 * 8; sc.cv[c].c1 = m1 * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS;
     }
     const int X0 = m0 * 8 * MT::H;           // first luma column of the tile
     const int tw = tm * 8 * MT::H;           // luma columns in the tile
@@ -404,56 +567,104 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     const u32 n_norm = im.n_norm, T = im.T, P = im.P;
     const bool ycc = im.out_kind == OUT_YCC;
     const int hv_avx = (int)im.hv_avx;
+    sc.sY = sY; sc.twy = TWY; sc.X0 = X0; sc.Wp = Wp; sc.hv_avx = hv_avx; sc.y_base = y_base; sc.height = im.height;
+    sc.stride = stride; sc.n_norm = n_norm; sc.T = T; sc.ycc = ycc; sc.out = out; sc.width = im.width; sc.nc = im.nc;
 
     if (im.small_width) {
-        // width < 16: the first 16 samples (zero-padded past Wp) are converted into a 16*nc-byte temp and its
-        // first width*nc bytes are copied out (worker.rs:176-198).  A single tile covers the row.
-        const u32 rowbytes = im.width * im.nc;
-        for (int u = tid; u < ROWS * 16; u += ZJ_THREADS) {
-            const int yl = u >> 4, s = u & 15;
-            const u32 y = y_base + yl;
-            if (y >= im.height) continue;
-            int yy = 0, cb = 0, cr = 0;
-            if (s < Wp) {
-                yy = (int)sY[yl * TWY + s];
-                cb = chroma_at<MODE, VARIANT, ST>(cv[0], yl, s, Wp, hv_avx);
-                cr = chroma_at<MODE, VARIANT, ST>(cv[1], yl, s, Wp, hv_avx);
-            }
-            u32 px[3];
-            ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
-            uint8_t *row = out + (size_t)y * stride;
-#pragma unroll
-            for (int c = 0; c < 3; c++) { const u32 b = 3 * s + c; if (b < rowbytes) row[b] = (uint8_t)px[c]; }
-            if (s == 0) for (u32 b = 48; b < rowbytes; b++) row[b] = 0;
-        }
+        slow_small_width<MODE, VARIANT, ST>(sc, ROWS, tid);
         return;
     }
 
-    for (int u = tid; u < ROWS * (tw >> 3); u += ZJ_THREADS) {
-        const int yl = u / (tw >> 3);
-        const int xl = (u - yl * (tw >> 3)) << 3;  // tile-local luma column of this 8-sample unit
-        const u32 y = y_base + yl;
-        if (y >= im.height) continue;              // rows past the image are truncated (mcu.rs:375)
-        uint8_t *row = out + (size_t)y * stride;
-#pragma unroll 1
-        for (int k = 0; k < 8; k++) {
-            const int s = X0 + xl + k;             // sample (luma column) in the padded row
-            const bool normal = (u32)s < n_norm;
-            const bool tail = (T != 0xffffffffu) && s >= Wp - 16;
-            if (!normal && !tail) continue;
-            const int yy = (int)sY[yl * TWY + xl + k];
-            const int cb = chroma_at<MODE, VARIANT, ST>(cv[0], yl, s, Wp, hv_avx);
-            const int cr = chroma_at<MODE, VARIANT, ST>(cv[1], yl, s, Wp, hv_avx);
-            u32 px[3];
-            if (ycc) { px[0] = (u32)yy & 0xff; px[1] = (u32)cb & 0xff; px[2] = (u32)cr & 0xff; }  // `as u8`
-            else ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
-            if (normal) {
+    // A unit is 8 luma columns of one output row (NONE, H) or of the two rows that share their chroma inputs
+    // (V: rows 2k,2k+1; HV: rows 4j+p and 4j+p+2, the near and far results of chroma row 2j+p).
+    constexpr int RPU = (MODE == MODE_V || MODE == MODE_HV) ? 2 : 1;   // rows per unit
+    constexpr int NRU = ROWS / RPU;                                    // row groups per strip
+    const int xunits = tw >> 3;
+    const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && (MODE != MODE_HV || hv_avx);
+    const bool align8 = (stride & 7u) == 0;
+    for (int u = tid; u < NRU * xunits; u += ZJ_THREADS) {
+        const int rg = u / xunits;
+        const int xl = (u - rg * xunits) << 3;
+        const int xs = X0 + xl;                    // first sample of the unit in the padded row
+        int yl0, yl1;                              // strip rows of the unit
+        if (MODE == MODE_V) { yl0 = 2 * rg; yl1 = yl0 + 1; }
+        else if (MODE == MODE_HV) { yl0 = 4 * (rg >> 1) + (rg & 1); yl1 = yl0 + 2; }
+        else { yl0 = rg; yl1 = rg; }
+        // fast path only for units whose 24 output bytes are plain "normal" bytes of the row writer ...
+        bool fast = fast_ok && (u32)(xs + 8) <= n_norm && !((u32)(3 * xs + 24) > T && (u32)(3 * xs) < T + 48);
+        const int cc0 = xs >> 1;                   // first chroma column (H, HV)
+        int l0 = 0;
+        if (MODE == MODE_H || MODE == MODE_HV) {
+            // ... and whose chroma window cc0-1 .. cc0+4 stays inside one image row (the flat filters wrap across
+            // row ends there, Q4a; upsampler/sse.rs' strip tail Q4b is the last unit of the last row)
+            fast = fast && cc0 >= 4 && cc0 + 4 < W;
+        }
+        if (MODE == MODE_HV) {
+            const int p = rg & 1;
+            l0 = (p * W + cc0) & 15;               // AVX2 lane of the unit's first sample
+            // not the raw-input tail of odd rows (Q4g) and not lane 15 of a double-row's first vector (Q4f)
+            fast = fast && !(p == 1 && cc0 + 4 > W - 16) && !(p == 0 && cc0 == 12);
+        }
+        if (!fast) {
+            slow_row8<MODE, VARIANT, ST>(sc, yl0, xl);
+            if (RPU == 2) slow_row8<MODE, VARIANT, ST>(sc, yl1, xl);
+            continue;
+        }
+        if constexpr (VARIANT == 0) {
+            u32 cb0[4], cr0[4], cb1[4], cr1[4];    // chroma lane pairs of row 0 / row 1 of the unit
 #pragma unroll
-                for (int c = 0; c < 3; c++) { const u32 b = 3 * s + c; if (!(b >= T && b < T + 48)) row[b] = (uint8_t)px[c]; }
+            for (int c = 0; c < 2; c++) {
+                u32 *o0 = c == 0 ? cb0 : cr0, *o1 = c == 0 ? cb1 : cr1;
+                const uint8_t *base = reinterpret_cast<const uint8_t *>(sC[c]);
+                if (MODE == MODE_NONE) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(base + yl0 * CS + 8 + xl);
+                    o0[0] = lanes01(v.x); o0[1] = lanes23(v.x); o0[2] = lanes01(v.y); o0[3] = lanes23(v.y);
+                } else if (MODE == MODE_V) {
+                    // rows 2k, 2k+1 <- T(r_k, r_k+1), T(r_k+1, r_k); first and last pair replicate (scalar.rs:64-147)
+                    const int ka = rg == 0 ? 0 : (rg == 7 ? 7 : rg), kb = rg == 0 ? 0 : (rg == 7 ? 7 : rg + 1);
+                    const uint2 va = *reinterpret_cast<const uint2 *>(base + ka * CS + 8 + xl);
+                    const uint2 vb = *reinterpret_cast<const uint2 *>(base + kb * CS + 8 + xl);
+                    const u32 a[4] = {lanes01(va.x), lanes23(va.x), lanes01(va.y), lanes23(va.y)};
+                    const u32 b[4] = {lanes01(vb.x), lanes23(vb.x), lanes01(vb.y), lanes23(vb.y)};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { o0[k] = T2(a[k], b[k]); o1[k] = T2(b[k], a[k]); }
+                } else {
+                    const int lc = 8 + (cc0 - m0 * 8);  // smem column of cc0 (multiple of 4)
+                    if (MODE == MODE_H) {
+                        const u32 *pa = reinterpret_cast<const u32 *>(base + yl0 * CS + lc);
+                        const u32 w0 = pa[-1], w1 = pa[0], w2 = pa[1];
+                        hfilter8(prmt(w0, w2, 0x0403u) & 0x00ff00ffu, lanes01(w1), lanes23(w1), o0);
+                    } else {
+                        // chroma row 2j+p blended with row 2j+p+2 (same row for the first / last double-row)
+                        const int j = rg >> 1, ra = 2 * j + (rg & 1), rb = (j == 0 || j == 7) ? ra : ra + 2;
+                        const u32 *pa = reinterpret_cast<const u32 *>(base + ra * CS + lc);
+                        const u32 *pb = reinterpret_cast<const u32 *>(base + rb * CS + lc);
+                        const u32 a0 = pa[-1], a1 = pa[0], a2 = pa[1], b0 = pb[-1], b1 = pb[0], b2 = pb[1];
+                        const u32 Aa = lanes01(a1), Ab = lanes23(a1), Ah = prmt(a0, a2, 0x0403u) & 0x00ff00ffu;
+                        const u32 Ba = lanes01(b1), Bb = lanes23(b1), Bh = prmt(b0, b2, 0x0403u) & 0x00ff00ffu;
+                        u32 Nh = T2(Ah, Bh), Fh = T2(Bh, Ah);
+                        if (l0 == 0) {   // lane 0: the "previous" value is 3*(in+in'+2)>>2 of the vector's OWN first element (Q4e)
+                            const u32 pv = (3u * ((Aa & 0xffffu) + (Ba & 0xffffu) + 2u)) >> 2;
+                            Nh = (Nh & 0xffff0000u) | pv; Fh = (Fh & 0xffff0000u) | pv;
+                        }
+                        if (l0 == 12) {  // lane 15: the "next" value is 3*(in+in'+2)>>2 of the next vector's first element
+                            const u32 pf = (3u * ((Ah >> 16) + (Bh >> 16) + 2u)) >> 2;
+                            Nh = (Nh & 0xffffu) | (pf << 16); Fh = (Fh & 0xffffu) | (pf << 16);
+                        }
+                        hfilter8(Nh, T2(Aa, Ba), T2(Ab, Bb), o0);
+                        hfilter8(Fh, T2(Ba, Aa), T2(Bb, Ab), o1);
+                    }
+                }
             }
-            if (tail) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) row[T + 3 * (s - (Wp - 16)) + c] = (uint8_t)px[c];
+            const uint8_t *ybase = reinterpret_cast<const uint8_t *>(sY);
+            u32 yv[4];
+            if (y_base + yl0 < im.height) {
+                load_y8(ybase + yl0 * TWY + xl, yv);
+                emit8(out + (size_t)(y_base + yl0) * stride + 3 * xs, yv, cb0, cr0, ycc, align8);
+            }
+            if (RPU == 2 && y_base + yl1 < im.height) {
+                load_y8(ybase + yl1 * TWY + xl, yv);
+                emit8(out + (size_t)(y_base + yl1) * stride + 3 * xs, yv, cb1, cr1, ycc, align8);
             }
         }
     }
