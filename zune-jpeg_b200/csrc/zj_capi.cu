@@ -158,6 +158,9 @@ static int plan_image(const zj_image *img, Plan *pl)
         const int tmv[4] = {TM_NONE, TM_H, TM_V, TM_HV};
         d.n_tiles = (mcu_x + tmv[mode] - 1) / tmv[mode];
         pl->grid_tiles = d.n_tiles;
+        d.tile_q = mcu_x / d.n_tiles;
+        d.tile_r = mcu_x % d.n_tiles;
+        d.magic_w = d.W ? (((uint64_t)1 << 40) + d.W - 1) / d.W : 0;
     }
     return ZJ_OK;
 }

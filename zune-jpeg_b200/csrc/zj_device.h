@@ -21,6 +21,7 @@ enum OutKind : int {
 //   NONE: 3 blocks  -> TM 40 -> 120                   H: 8 -> TM 15 -> 120 + 8
 //   V:    4 blocks  -> TM 32 -> 128                   HV: 12 -> TM 10 -> 120 + 8 (+4 in tile 0)
 constexpr int ZJ_THREADS = 128;
+constexpr int ZJ_SLOW_CAP = 192;  // edge units per tile queued for the generic path
 constexpr int TM_NONE = 40, TM_H = 15, TM_V = 32, TM_HV = 10, TM_GRAY = 128;
 
 struct DevImage {
@@ -43,6 +44,8 @@ struct DevImage {
     uint32_t small_width;     // width < 16: temp-buffer path (worker.rs:158-163,176-198)
     uint32_t hv_avx;          // HV + X86 + chroma strip >= 500 samples -> AVX2 closed form
     uint32_t gray_rows_ok;    // Q7 resolved: 1 = plain row copy is what the reference does
+    uint32_t tile_q, tile_r;  // tile t covers MCU columns [t*q + min(t,r), ...): the first r tiles are one column wider
+    uint64_t magic_w;         // ceil(2^40 / W): idx / W == (idx * magic_w) >> 40 for idx < 2^20
 };
 
 // Host-side launch plan entry: one kernel launch per (mode, variant, out-kind class) group.

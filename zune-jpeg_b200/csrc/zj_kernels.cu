@@ -161,7 +161,8 @@ struct ChromaView {
     int c0, c1;      // tile column range [c0, c1)
     int lhb, rhb, spb;  // block columns held in the left / right / special halo slots (-1 = none)
     int cs;          // smem row stride (samples)
-    __device__ __forceinline__ int at(int row, int col) const
+    unsigned long long magic_w;  // ceil(2^40 / W)
+    __device__ __noinline__ int at(int row, int col) const
     {
         int lc;
         if (col >= c0 && col < c1) lc = 8 + (col - c0);
@@ -172,7 +173,7 @@ struct ChromaView {
     }
     __device__ __forceinline__ int flat(int idx) const
     {
-        int row = idx / W;
+        const int row = (int)(((unsigned long long)(unsigned)idx * magic_w) >> 40);  // idx / W without a divide
         return at(row, idx - row * W);
     }
     // `.get(i).unwrap_or(&0)` of upsampler/avx2.rs:264-270
@@ -225,7 +226,7 @@ template <typename ST>
 __device__ int hv_vo(const ChromaView<ST> &v, int f)
 {
     const int S = 2 * v.W;
-    const int d = f / S, i = f - d * S, k = d >> 1;
+    const int d = (int)(((unsigned long long)(unsigned)f * v.magic_w) >> 40) >> 1, i = f - d * S, k = d >> 1;  // f / (2W)
     if (d < 2) return v.flat(i);
     if (d >= 14) return v.flat(7 * S + i);
     const int a = v.flat(k * S + i), b = v.flat((k + 1) * S + i);
@@ -249,7 +250,7 @@ __device__ int up_hv_avx(const ChromaView<ST> &v, int o)
 {
     const int S = v.n >> 3;  // input double-row length = 2W
     const int L = 2 * S;     // output double-row length
-    const int d2 = o / L;
+    const int d2 = (int)(((unsigned long long)(unsigned)o * v.magic_w) >> 40) >> 2;  // o / (4W)
     int e = o - d2 * L;
     const int j = d2 >> 1, far = d2 & 1;
     const int sj = (j == 0 || j == 7) ? 0 : S;
@@ -322,32 +323,29 @@ struct SlowCtx {
 };
 
 template <int MODE, int VARIANT, typename ST>
-__device__ __noinline__ void slow_row8(const SlowCtx<ST> &c, int yl, int xl)
+__device__ __noinline__ void slow_pixel(const SlowCtx<ST> &c, int yl, int x)  // x = tile-local luma column
 {
     const u32 y = c.y_base + yl;
     if (y >= c.height) return;                 // rows past the image are truncated (mcu.rs:375)
     uint8_t *row = c.out + (size_t)y * c.stride;
     const u32 T = c.T;
-#pragma unroll 1
-    for (int k = 0; k < 8; k++) {
-        const int s = c.X0 + xl + k;           // sample (luma column) in the padded row
-        const bool normal = (u32)s < c.n_norm;
-        const bool tail = (T != 0xffffffffu) && s >= c.Wp - 16;
-        if (!normal && !tail) continue;
-        const int yy = (int)c.sY[yl * c.twy + xl + k];
-        const int cb = chroma_at<MODE, VARIANT, ST>(c.cv[0], yl, s, c.Wp, c.hv_avx);
-        const int cr = chroma_at<MODE, VARIANT, ST>(c.cv[1], yl, s, c.Wp, c.hv_avx);
-        u32 px[3];
-        if (c.ycc) { px[0] = (u32)yy & 0xff; px[1] = (u32)cb & 0xff; px[2] = (u32)cr & 0xff; }  // `as u8`
-        else ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
-        if (normal) {
+    const int s = c.X0 + x;                    // sample (luma column) in the padded row
+    const bool normal = (u32)s < c.n_norm;
+    const bool tail = (T != 0xffffffffu) && s >= c.Wp - 16;
+    if (!normal && !tail) return;
+    const int yy = (int)c.sY[yl * c.twy + x];
+    const int cb = chroma_at<MODE, VARIANT, ST>(c.cv[0], yl, s, c.Wp, c.hv_avx);
+    const int cr = chroma_at<MODE, VARIANT, ST>(c.cv[1], yl, s, c.Wp, c.hv_avx);
+    u32 px[3];
+    if (c.ycc) { px[0] = (u32)yy & 0xff; px[1] = (u32)cb & 0xff; px[2] = (u32)cr & 0xff; }  // `as u8`
+    else ycc_to_rgb(yy, cb, cr, px[0], px[1], px[2]);
+    if (normal) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) { const u32 b = 3 * s + ch; if (!(b >= T && b < T + 48)) row[b] = (uint8_t)px[ch]; }
-        }
-        if (tail) {
+        for (int ch = 0; ch < 3; ch++) { const u32 b = 3 * s + ch; if (!(b >= T && b < T + 48)) row[b] = (uint8_t)px[ch]; }
+    }
+    if (tail) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) row[T + 3 * (s - (c.Wp - 16)) + ch] = (uint8_t)px[ch];
-        }
+        for (int ch = 0; ch < 3; ch++) row[T + 3 * (s - (c.Wp - 16)) + ch] = (uint8_t)px[ch];
     }
 }
 
@@ -468,7 +466,7 @@ __device__ __forceinline__ void load_y8(const uint8_t *p, u32 y[4])
 // --------------------------------------------------------------------------------------- the fused kernel
 // grid = (tiles, strips [+1 when rows are dropped], images of this launch group); block = ZJ_THREADS.
 template <int MODE, int VARIANT>
-__global__ void __launch_bounds__(ZJ_THREADS)
+__global__ void __launch_bounds__(ZJ_THREADS, 5)
 reconstruct_kernel(const DevImage *__restrict__ images)
 {
     typedef ModeTraits<MODE> MT;
@@ -484,6 +482,8 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     __shared__ __align__(16) ST sY[YROWS * TWY];
     __shared__ __align__(16) ST sC[2][CROWS * CS];
     __shared__ u32 sQ[3][32];
+    __shared__ int sSlowN;
+    __shared__ unsigned short sSlow[ZJ_SLOW_CAP];  // edge units left to the generic path (row group << 8 | x unit)
 
     const DevImage &im = images[blockIdx.z];
     const u32 tile = blockIdx.x, strip = blockIdx.y;
@@ -504,14 +504,15 @@ reconstruct_kernel(const DevImage *__restrict__ images)
         return;
     }
 
-    // tile -> MCU column range, spread evenly so that every tile keeps >= TM/2 columns
+    // tile -> MCU column range, spread evenly (first tile_r tiles one column wider) so every tile keeps >= TM/2 columns
     const int mcu_x = (int)im.mcu_x, nt = (int)im.n_tiles;
-    const int m0 = (int)(((long long)tile * mcu_x) / nt), m1 = (int)(((long long)(tile + 1) * mcu_x) / nt);
+    const int m0 = (int)(tile * im.tile_q + min(tile, im.tile_r)), m1 = (int)((tile + 1) * im.tile_q + min(tile + 1, im.tile_r));
     const int tm = m1 - m0;                      // MCU columns in this tile (<= TM)
     const int Wp = (int)im.Wp, W = (int)im.W;
     const int ybpr = MT::H * mcu_x;              // luma blocks per block-row of the plane
 
     for (int k = tid; k < 96; k += ZJ_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
+    if (tid == 0) sSlowN = 0;
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 1: IDCT into shared planes
@@ -558,7 +559,7 @@ reconstruct_kernel(const DevImage *__restrict__ images)
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         sc.cv[c].base = sC[c]; sc.cv[c].W = W; sc.cv[c].n = CROWS * W;
-        sc.cv[c].c0 = m0 * 8; sc.cv[c].c1 = m1 * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS;
+        sc.cv[c].c0 = m0 * 8; sc.cv[c].c1 = m1 * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS; sc.cv[c].magic_w = im.magic_w;
     }
     const int X0 = m0 * 8 * MT::H;           // first luma column of the tile
     const int tw = tm * 8 * MT::H;           // luma columns in the tile
@@ -582,23 +583,32 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     const int xunits = tw >> 3;
     const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && (MODE != MODE_HV || hv_avx);
     const bool align8 = (stride & 7u) == 0;
-    for (int u = tid; u < NRU * xunits; u += ZJ_THREADS) {
-        const int rg = u / xunits;
-        const int xl = (u - rg * xunits) << 3;
-        const int xs = X0 + xl;                    // first sample of the unit in the padded row
+    if (!fast_ok) {
+        // SCALAR variant (i16 samples, unclamped DC-only values), odd strides, tiny 4:2:0 images: every sample
+        // takes the generic path, one sample per thread
+        for (int u = tid; u < ROWS * tw; u += ZJ_THREADS) {
+            const int yl = u / tw;
+            slow_pixel<MODE, VARIANT, ST>(sc, yl, u - yl * tw);
+        }
+    }
+    // thread -> fixed x unit, loop over row groups: everything that depends only on the column is hoisted
+    const int rpp = ZJ_THREADS / xunits;           // row groups per pass
+    const int xu = tid % xunits, r0 = tid / xunits;
+    const int xl = xu << 3;
+    const int xs = X0 + xl;                        // first sample of the unit in the padded row
+    const int cc0 = xs >> 1;                       // first chroma column (H, HV)
+    // fast path only for units whose 24 output bytes are plain "normal" bytes of the row writer ...
+    bool fastx = (u32)(xs + 8) <= n_norm && !((u32)(3 * xs + 24) > T && (u32)(3 * xs) < T + 48);
+    // ... and whose chroma window cc0-1 .. cc0+4 stays inside one image row (the flat filters wrap across row
+    // ends there, Q4a; upsampler/sse.rs' strip tail Q4b is the last unit of the last row)
+    if (MODE == MODE_H || MODE == MODE_HV) fastx = fastx && cc0 >= 4 && cc0 + 4 < W;
+    for (int rg = r0; fast_ok && r0 < rpp && rg < NRU; rg += rpp) {
         int yl0, yl1;                              // strip rows of the unit
         if (MODE == MODE_V) { yl0 = 2 * rg; yl1 = yl0 + 1; }
         else if (MODE == MODE_HV) { yl0 = 4 * (rg >> 1) + (rg & 1); yl1 = yl0 + 2; }
         else { yl0 = rg; yl1 = rg; }
-        // fast path only for units whose 24 output bytes are plain "normal" bytes of the row writer ...
-        bool fast = fast_ok && (u32)(xs + 8) <= n_norm && !((u32)(3 * xs + 24) > T && (u32)(3 * xs) < T + 48);
-        const int cc0 = xs >> 1;                   // first chroma column (H, HV)
+        bool fast = fastx;
         int l0 = 0;
-        if (MODE == MODE_H || MODE == MODE_HV) {
-            // ... and whose chroma window cc0-1 .. cc0+4 stays inside one image row (the flat filters wrap across
-            // row ends there, Q4a; upsampler/sse.rs' strip tail Q4b is the last unit of the last row)
-            fast = fast && cc0 >= 4 && cc0 + 4 < W;
-        }
         if (MODE == MODE_HV) {
             const int p = rg & 1;
             l0 = (p * W + cc0) & 15;               // AVX2 lane of the unit's first sample
@@ -606,8 +616,13 @@ reconstruct_kernel(const DevImage *__restrict__ images)
             fast = fast && !(p == 1 && cc0 + 4 > W - 16) && !(p == 0 && cc0 == 12);
         }
         if (!fast) {
-            slow_row8<MODE, VARIANT, ST>(sc, yl0, xl);
-            if (RPU == 2) slow_row8<MODE, VARIANT, ST>(sc, yl1, xl);
+            // edge unit: queue it; all threads share the queued samples after the loop (a warp that ran the
+            // generic code inline would serialise ~10^4 instructions behind one or two active lanes)
+            const int slot = atomicAdd(&sSlowN, 1);
+            if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)((rg << 8) | xu);
+            else {
+                for (int k = 0; k < 8; k++) { slow_pixel<MODE, VARIANT, ST>(sc, yl0, xl + k); if (RPU == 2) slow_pixel<MODE, VARIANT, ST>(sc, yl1, xl + k); }
+            }
             continue;
         }
         if constexpr (VARIANT == 0) {
@@ -643,14 +658,14 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                         const u32 Aa = lanes01(a1), Ab = lanes23(a1), Ah = prmt(a0, a2, 0x0403u) & 0x00ff00ffu;
                         const u32 Ba = lanes01(b1), Bb = lanes23(b1), Bh = prmt(b0, b2, 0x0403u) & 0x00ff00ffu;
                         u32 Nh = T2(Ah, Bh), Fh = T2(Bh, Ah);
-                        if (l0 == 0) {   // lane 0: the "previous" value is 3*(in+in'+2)>>2 of the vector's OWN first element (Q4e)
-                            const u32 pv = (3u * ((Aa & 0xffffu) + (Ba & 0xffffu) + 2u)) >> 2;
-                            Nh = (Nh & 0xffff0000u) | pv; Fh = (Fh & 0xffff0000u) | pv;
-                        }
-                        if (l0 == 12) {  // lane 15: the "next" value is 3*(in+in'+2)>>2 of the next vector's first element
-                            const u32 pf = (3u * ((Ah >> 16) + (Bh >> 16) + 2u)) >> 2;
-                            Nh = (Nh & 0xffffu) | (pf << 16); Fh = (Fh & 0xffffu) | (pf << 16);
-                        }
+                        // lane 0: the "previous" value is 3*(in+in'+2)>>2 of the vector's OWN first element (Q4e);
+                        // lane 15: the "next" value is the same expression on the next vector's first element
+                        const u32 pv = (3u * ((Aa & 0xffffu) + (Ba & 0xffffu) + 2u)) >> 2;
+                        const u32 pf = ((3u * ((Ah >> 16) + (Bh >> 16) + 2u)) >> 2) << 16;
+                        const u32 keep = (l0 == 0 ? 0xffff0000u : 0xffffffffu) & (l0 == 12 ? 0x0000ffffu : 0xffffffffu);
+                        const u32 ins = (l0 == 0 ? pv : 0u) | (l0 == 12 ? pf : 0u);
+                        Nh = (Nh & keep) | ins;
+                        Fh = (Fh & keep) | ins;
                         hfilter8(Nh, T2(Aa, Ba), T2(Ab, Bb), o0);
                         hfilter8(Fh, T2(Ba, Aa), T2(Bb, Ab), o1);
                     }
@@ -666,6 +681,19 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                 load_y8(ybase + yl1 * TWY + xl, yv);
                 emit8(out + (size_t)(y_base + yl1) * stride + 3 * xs, yv, cb1, cr1, ycc, align8);
             }
+        }
+    }
+    if (fast_ok) {
+        __syncthreads();
+        const int nslow = min(sSlowN, ZJ_SLOW_CAP);
+        for (int t = tid; t < nslow * 8 * RPU; t += ZJ_THREADS) {
+            const int e = sSlow[t / (8 * RPU)], r = (t >> 3) % RPU, k = t & 7;
+            const int rg = e >> 8, xl = (e & 0xff) << 3;
+            int yl;
+            if (MODE == MODE_V) yl = 2 * rg + r;
+            else if (MODE == MODE_HV) yl = 4 * (rg >> 1) + (rg & 1) + 2 * r;
+            else yl = rg;
+            slow_pixel<MODE, VARIANT, ST>(sc, yl, xl + k);
         }
     }
     // bytes of the row nobody writes: [P, stride) minus the tail chunk (Q5: 16 zero bytes; Q6: the w "alpha" bytes)
