@@ -436,7 +436,7 @@ __device__ __forceinline__ void pack24(const u32 c0[4], const u32 c1[4], const u
     }
 }
 
-__device__ __forceinline__ void emit8(uint8_t *dst, const u32 y[4], const u32 cb[4], const u32 cr[4], bool ycc, bool align8)
+__device__ __forceinline__ void emit8(uint8_t *dst, const u32 y[4], const u32 cb[4], const u32 cr[4], bool ycc, int nwords)
 {
     u32 w[6];
     if (ycc) {
@@ -447,13 +447,13 @@ __device__ __forceinline__ void emit8(uint8_t *dst, const u32 y[4], const u32 cb
         for (int k = 0; k < 4; k++) convert_pair(y[k], cb[k], cr[k], r[k], g[k], b[k]);
         pack24(r, g, b, w);
     }
-    if (align8) {
+    if (nwords == 6 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         uint2 *d = reinterpret_cast<uint2 *>(dst);
         d[0] = make_uint2(w[0], w[1]); d[1] = make_uint2(w[2], w[3]); d[2] = make_uint2(w[4], w[5]);
     } else {
         u32 *d = reinterpret_cast<u32 *>(dst);
 #pragma unroll
-        for (int k = 0; k < 6; k++) d[k] = w[k];
+        for (int k = 0; k < 6; k++) if (k < nwords) d[k] = w[k];
     }
 }
 
@@ -582,7 +582,6 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     constexpr int NRU = ROWS / RPU;                                    // row groups per strip
     const int xunits = tw >> 3;
     const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && (MODE != MODE_HV || hv_avx);
-    const bool align8 = (stride & 7u) == 0;
     if (!fast_ok) {
         // SCALAR variant (i16 samples, unclamped DC-only values), odd strides, tiny 4:2:0 images: every sample
         // takes the generic path, one sample per thread
@@ -597,24 +596,48 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     const int xl = xu << 3;
     const int xs = X0 + xl;                        // first sample of the unit in the padded row
     const int cc0 = xs >> 1;                       // first chroma column (H, HV)
-    // fast path only for units whose 24 output bytes are plain "normal" bytes of the row writer ...
-    bool fastx = (u32)(xs + 8) <= n_norm && !((u32)(3 * xs + 24) > T && (u32)(3 * xs) < T + 48);
-    // ... and whose chroma window cc0-1 .. cc0+4 stays inside one image row (the flat filters wrap across row
-    // ends there, Q4a; upsampler/sse.rs' strip tail Q4b is the last unit of the last row)
-    if (MODE == MODE_H || MODE == MODE_HV) fastx = fastx && cc0 >= 4 && cc0 + 4 < W;
+    // Where the unit's 24 bytes go in the output row (worker.rs:201-246):
+    //   samples < n_norm ("normal" 16-sample chunks) sit at byte 3*s, except bytes the tail chunk overwrites;
+    //   samples >= Wp-16 (the tail chunk) sit at T + 3*(s - (Wp-16));  anything else is never written.
+    int dst_off = 3 * xs;
+    int nwords = 6;                                // words of the unit to store; 0 = nothing; -1 = leave to the generic path
+    if ((u32)(xs + 8) <= n_norm) {
+        if ((u32)(3 * xs + 24) > T && (u32)(3 * xs) < T + 48) {        // overlaps the tail chunk's bytes [T, T+48)
+            const int keep = (int)T - 3 * xs;                            // bytes before T survive
+            nwords = (keep > 0 && (keep & 3) == 0 && (u32)(3 * xs + 24) <= T + 48) ? (keep >> 2) : (keep <= 0 && (u32)(3 * xs + 24) <= T + 48 ? 0 : -1);
+        }
+    } else if (T != 0xffffffffu && xs >= Wp - 16) {
+        dst_off = (int)T + 3 * (xs - (Wp - 16));
+    } else if ((u32)xs >= n_norm && (T == 0xffffffffu || xs + 8 <= Wp - 16)) {
+        nwords = 0;                                                      // e.g. the 8 samples between the last chunk and the tail when Wp % 16 == 8
+    } else {
+        nwords = -1;
+    }
+    if ((dst_off & 3) != 0) nwords = nwords > 0 ? -1 : nwords;
+    // chroma window cc0-1 .. cc0+4: the flat filters run across image-row ends (Q4a), so the first / last unit of a
+    // row takes its outer neighbour from the previous / next chroma row, which is what the wrapped halo blocks hold
+    const bool first_x = (MODE == MODE_H || MODE == MODE_HV) && cc0 == 0;
+    const bool last_x = (MODE == MODE_H || MODE == MODE_HV) && cc0 + 4 == W;
     for (int rg = r0; fast_ok && r0 < rpp && rg < NRU; rg += rpp) {
         int yl0, yl1;                              // strip rows of the unit
         if (MODE == MODE_V) { yl0 = 2 * rg; yl1 = yl0 + 1; }
         else if (MODE == MODE_HV) { yl0 = 4 * (rg >> 1) + (rg & 1); yl1 = yl0 + 2; }
         else { yl0 = rg; yl1 = rg; }
-        bool fast = fastx;
+        bool fast = nwords >= 0;
         int l0 = 0;
+        bool hv_tail = false;
+        if (MODE == MODE_H) {
+            // strip start (out[0], out[1] edge rule) and strip end (scalar.rs:46-57 / the SSE tail Q4b) stay generic
+            fast = fast && !(first_x && rg == 0) && !(last_x && rg == NRU - 1);
+        }
         if (MODE == MODE_HV) {
             const int p = rg & 1;
             l0 = (p * W + cc0) & 15;               // AVX2 lane of the unit's first sample
-            // not the raw-input tail of odd rows (Q4g) and not lane 15 of a double-row's first vector (Q4f)
-            fast = fast && !(p == 1 && cc0 + 4 > W - 16) && !(p == 0 && cc0 == 12);
+            hv_tail = p == 1 && cc0 + 4 > W - 16;  // last 32 outputs of an odd row: raw input shifted 17 samples left (Q4g)
+            // generic: the first vector of a double-row (stale lane-0 / lane-15 neighbours, Q4f; out[0] of far rows)
+            fast = fast && !(p == 0 && (cc0 == 0 || cc0 == 12)) && !(hv_tail && W - 36 < m0 * 8);
         }
+        if (nwords == 0 && fast) continue;         // nothing of this unit is ever written
         if (!fast) {
             // edge unit: queue it; all threads share the queued samples after the loop (a warp that ran the
             // generic code inline would serialise ~10^4 instructions behind one or two active lanes)
@@ -645,16 +668,31 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                     for (int k = 0; k < 4; k++) { o0[k] = T2(a[k], b[k]); o1[k] = T2(b[k], a[k]); }
                 } else {
                     const int lc = 8 + (cc0 - m0 * 8);  // smem column of cc0 (multiple of 4)
+                    // outer neighbours of the first / last unit of a row live one chroma row up / down (flat array)
+                    const int off0 = first_x ? -CS : 0, off2 = last_x ? CS : 0;
                     if (MODE == MODE_H) {
-                        const u32 *pa = reinterpret_cast<const u32 *>(base + yl0 * CS + lc);
-                        const u32 w0 = pa[-1], w1 = pa[0], w2 = pa[1];
+                        const uint8_t *pa = base + yl0 * CS + lc;
+                        const u32 w0 = *reinterpret_cast<const u32 *>(pa - 4 + off0), w1 = *reinterpret_cast<const u32 *>(pa), w2 = *reinterpret_cast<const u32 *>(pa + 4 + off2);
                         hfilter8(prmt(w0, w2, 0x0403u) & 0x00ff00ffu, lanes01(w1), lanes23(w1), o0);
+                    } else if (hv_tail) {
+                        // out[O+2k] = T(in[c], in[c-1]), out[O+2k+1] = T(in[c], in[c+1]), c = (row end) - 33 + k: no vertical
+                        // blend, raw row 2j+1 for the near row and row 2j+3 for the far row; k = 15 repeats k = 14
+                        // (upsampler/avx2.rs:277-307,332-338)
+                        const int j = rg >> 1, ra = 2 * j + 1, rb = (j == 0 || j == 7) ? ra : ra + 2;
+                        const int q = (cc0 - (W - 16)) >> 2;                  // which 8 of the 32 outputs
+                        const int lq = 8 + (W - 36 + 4 * q - m0 * 8);         // smem column of c - 3 for k = 4q (multiple of 4)
+                        const u32 *pa = reinterpret_cast<const u32 *>(base + ra * CS + lq);
+                        const u32 *pb = reinterpret_cast<const u32 *>(base + rb * CS + lq);
+                        const u32 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+                        hfilter8(prmt(a0, a1, 0x0702u) & 0x00ff00ffu, prmt(a0, a1, 0x0403u) & 0x00ff00ffu, prmt(a1, 0u, 0x4241u), o0);
+                        hfilter8(prmt(b0, b1, 0x0702u) & 0x00ff00ffu, prmt(b0, b1, 0x0403u) & 0x00ff00ffu, prmt(b1, 0u, 0x4241u), o1);
+                        if (q == 3) { o0[3] = o0[2]; o1[3] = o1[2]; }
                     } else {
                         // chroma row 2j+p blended with row 2j+p+2 (same row for the first / last double-row)
                         const int j = rg >> 1, ra = 2 * j + (rg & 1), rb = (j == 0 || j == 7) ? ra : ra + 2;
-                        const u32 *pa = reinterpret_cast<const u32 *>(base + ra * CS + lc);
-                        const u32 *pb = reinterpret_cast<const u32 *>(base + rb * CS + lc);
-                        const u32 a0 = pa[-1], a1 = pa[0], a2 = pa[1], b0 = pb[-1], b1 = pb[0], b2 = pb[1];
+                        const uint8_t *pa = base + ra * CS + lc, *pb = base + rb * CS + lc;
+                        const u32 a0 = *reinterpret_cast<const u32 *>(pa - 4 + off0), a1 = *reinterpret_cast<const u32 *>(pa), a2 = *reinterpret_cast<const u32 *>(pa + 4 + off2);
+                        const u32 b0 = *reinterpret_cast<const u32 *>(pb - 4 + off0), b1 = *reinterpret_cast<const u32 *>(pb), b2 = *reinterpret_cast<const u32 *>(pb + 4 + off2);
                         const u32 Aa = lanes01(a1), Ab = lanes23(a1), Ah = prmt(a0, a2, 0x0403u) & 0x00ff00ffu;
                         const u32 Ba = lanes01(b1), Bb = lanes23(b1), Bh = prmt(b0, b2, 0x0403u) & 0x00ff00ffu;
                         u32 Nh = T2(Ah, Bh), Fh = T2(Bh, Ah);
@@ -675,11 +713,11 @@ reconstruct_kernel(const DevImage *__restrict__ images)
             u32 yv[4];
             if (y_base + yl0 < im.height) {
                 load_y8(ybase + yl0 * TWY + xl, yv);
-                emit8(out + (size_t)(y_base + yl0) * stride + 3 * xs, yv, cb0, cr0, ycc, align8);
+                emit8(out + (size_t)(y_base + yl0) * stride + dst_off, yv, cb0, cr0, ycc, nwords);
             }
             if (RPU == 2 && y_base + yl1 < im.height) {
                 load_y8(ybase + yl1 * TWY + xl, yv);
-                emit8(out + (size_t)(y_base + yl1) * stride + 3 * xs, yv, cb1, cr1, ycc, align8);
+                emit8(out + (size_t)(y_base + yl1) * stride + dst_off, yv, cb1, cr1, ycc, nwords);
             }
         }
     }
