@@ -192,6 +192,20 @@ static int set_device(int device)
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return ZJ_ERR_NO_DEVICE; }
     if (device < 0 || device >= n) return ZJ_ERR_NO_DEVICE;
     CU(cudaSetDevice(device));
+    // keep the stream-ordered pool's memory across calls: by default it is returned to the driver at every
+    // synchronisation, which makes each zj_gpu_reconstruct re-map gigabytes of staging memory
+    static std::mutex mu;
+    static bool tuned[64] = {false};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 64 && !tuned[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        tuned[device] = true;
+    }
     return ZJ_OK;
 }
 
