@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libzune_jpeg_b200.so")
+LIB_PATH = os.environ.get("ZJ_LIB_PATH") or os.path.join(_HERE, "csrc", "libzune_jpeg_b200.so")  # env override: tuning builds only
 
 # zj_colorspace / zj_variant / zj_status -------------------------------------------------------
 CS_RGB, CS_GRAYSCALE, CS_YCBCR, CS_CMYK, CS_YCCK, CS_RGBA, CS_RGBX = range(7)

@@ -18,11 +18,19 @@ enum OutKind : int {
 
 // MCU columns per tile, chosen so that one CTA of ZJ_THREADS threads has about one 8x8 block per thread
 // (including the chroma halo blocks):                 blocks / MCU column        + halo
-//   NONE: 3 blocks  -> TM 40 -> 120                   H: 8 -> TM 15 -> 120 + 8
+//   (per 128 threads) NONE: 3 blocks -> TM 40 -> 120  H: 8 -> TM 15 -> 120 + 8
 //   V:    4 blocks  -> TM 32 -> 128                   HV: 12 -> TM 10 -> 120 + 8 (+4 in tile 0)
-constexpr int ZJ_THREADS = 128;
+#ifndef ZJ_CFG_THREADS
+#define ZJ_CFG_THREADS 256
+#endif
+#ifndef ZJ_CFG_MINBLOCKS
+#define ZJ_CFG_MINBLOCKS 3
+#endif
+constexpr int ZJ_THREADS = ZJ_CFG_THREADS;
+constexpr int ZJ_MINBLOCKS = ZJ_CFG_MINBLOCKS;  // CTAs per SM the register allocation is capped for
 constexpr int ZJ_SLOW_CAP = 192;  // edge units per tile queued for the generic path
-constexpr int TM_NONE = 40, TM_H = 15, TM_V = 32, TM_HV = 10, TM_GRAY = 128;
+// tile widths scale with the CTA size (128 threads: 40 / 15 / 32 / 10)
+constexpr int TM_NONE = 40 * ZJ_THREADS / 128, TM_H = 15 * ZJ_THREADS / 128, TM_V = 32 * ZJ_THREADS / 128, TM_HV = 10 * ZJ_THREADS / 128, TM_GRAY = 128;
 
 struct DevImage {
     const int16_t *coeff[3];  // device pointers, whole-image planes

@@ -58,15 +58,22 @@ __device__ __forceinline__ u32 clamp255(u32 v) { return (u32)max(min((int)v, 255
 __device__ __forceinline__ u32 dp2a_lo(u32 a, u32 b) { u32 d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
 __device__ __forceinline__ u32 dp2a_hi(u32 a, u32 b) { u32 d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d; }
 
+// I2IP.U8.S32.SAT: d = (c << 16) | sat_u8(a) << 8 | sat_u8(b) -- clamp to [0,255] and pack two values per instruction
+__device__ __forceinline__ u32 pack_sat2(int hi, int lo, u32 upper) { u32 d; asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper)); return d; }
+// v[] are UNCLAMPED i32 results; the clamp of idct/avx2.rs:402-413 happens in the saturating pack
 __device__ __forceinline__ void store_row(uint8_t *dst, const u32 v[8])
 {
     uint2 w;
-    w.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-    w.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+    w.x = pack_sat2((int)v[1], (int)v[0], pack_sat2((int)v[3], (int)v[2], 0u));
+    w.y = pack_sat2((int)v[5], (int)v[4], pack_sat2((int)v[7], (int)v[6], 0u));
     *reinterpret_cast<uint2 *>(dst) = w;
 }
-__device__ __forceinline__ void store_row(int16_t *dst, const u32 v[8])
+template <bool CLAMP = true>
+__device__ __forceinline__ void store_row(int16_t *dst, const u32 vin[8])
 {
+    u32 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = CLAMP ? clamp255(vin[k]) : vin[k];
     uint4 w;
     w.x = (v[0] & 0xffffu) | (v[1] << 16);
     w.y = (v[2] & 0xffffu) | (v[3] << 16);
@@ -74,6 +81,10 @@ __device__ __forceinline__ void store_row(int16_t *dst, const u32 v[8])
     w.w = (v[6] & 0xffffu) | (v[7] << 16);
     *reinterpret_cast<uint4 *>(dst) = w;
 }
+
+// DC-only rows: X86 already clamped the value (the saturating pack is a no-op), SCALAR must stay unclamped
+__device__ __forceinline__ void store_dc_row(uint8_t *dst, const u32 v[8]) { store_row(dst, v); }
+__device__ __forceinline__ void store_dc_row(int16_t *dst, const u32 v[8]) { store_row<false>(dst, v); }
 
 // Dequantise + 2-D IDCT + level shift + clamp of one block; rows written to dst[r*dst_stride + 0..7].
 //   VARIANT 0 (X86):    pass A along rows, pass B down columns, DC-only value clamped   (idct/avx2.rs:64-398)
@@ -103,7 +114,7 @@ __device__ __forceinline__ void idct_block(const int16_t *__restrict__ src, cons
 #pragma unroll
         for (int k = 0; k < 8; k++) vv[k] = (u32)v;
 #pragma unroll
-        for (int r = 0; r < 8; r++) store_row(dst + r * dst_stride, vv);
+        for (int r = 0; r < 8; r++) store_dc_row(dst + r * dst_stride, vv);
         return;
     }
 
@@ -138,8 +149,8 @@ __device__ __forceinline__ void idct_block(const int16_t *__restrict__ src, cons
     for (int r = 0; r < 8; r++) {
         u32 vv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) vv[k] = clamp255(a[r * 8 + k]);
-        store_row(dst + r * dst_stride, vv);
+        for (int k = 0; k < 8; k++) vv[k] = a[r * 8 + k];
+        store_row(dst + r * dst_stride, vv);  // clamps
     }
 }
 
@@ -466,7 +477,7 @@ __device__ __forceinline__ void load_y8(const uint8_t *p, u32 y[4])
 // --------------------------------------------------------------------------------------- the fused kernel
 // grid = (tiles, strips [+1 when rows are dropped], images of this launch group); block = ZJ_THREADS.
 template <int MODE, int VARIANT>
-__global__ void __launch_bounds__(ZJ_THREADS, 5)
+__global__ void __launch_bounds__(ZJ_THREADS, ZJ_MINBLOCKS)
 reconstruct_kernel(const DevImage *__restrict__ images)
 {
     typedef ModeTraits<MODE> MT;
@@ -555,12 +566,6 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 2: up-sample, convert, write
-    SlowCtx<ST> sc;
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-        sc.cv[c].base = sC[c]; sc.cv[c].W = W; sc.cv[c].n = CROWS * W;
-        sc.cv[c].c0 = m0 * 8; sc.cv[c].c1 = m1 * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS; sc.cv[c].magic_w = im.magic_w;
-    }
     const int X0 = m0 * 8 * MT::H;           // first luma column of the tile
     const int tw = tm * 8 * MT::H;           // luma columns in the tile
     const bool last_tile = (tile + 1 == (u32)nt);
@@ -568,10 +573,20 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     const u32 n_norm = im.n_norm, T = im.T, P = im.P;
     const bool ycc = im.out_kind == OUT_YCC;
     const int hv_avx = (int)im.hv_avx;
-    sc.sY = sY; sc.twy = TWY; sc.X0 = X0; sc.Wp = Wp; sc.hv_avx = hv_avx; sc.y_base = y_base; sc.height = im.height;
-    sc.stride = stride; sc.n_norm = n_norm; sc.T = T; sc.ycc = ycc; sc.out = out; sc.width = im.width; sc.nc = im.nc;
+    // context of the generic path: built only by the CTAs that need it (edge tiles, SCALAR variant, ...)
+    auto make_ctx = [&](SlowCtx<ST> &sc) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            sc.cv[c].base = sC[c]; sc.cv[c].W = W; sc.cv[c].n = CROWS * W;
+            sc.cv[c].c0 = m0 * 8; sc.cv[c].c1 = m1 * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS; sc.cv[c].magic_w = im.magic_w;
+        }
+        sc.sY = sY; sc.twy = TWY; sc.X0 = X0; sc.Wp = Wp; sc.hv_avx = hv_avx; sc.y_base = y_base; sc.height = im.height;
+        sc.stride = stride; sc.n_norm = n_norm; sc.T = T; sc.ycc = ycc; sc.out = out; sc.width = im.width; sc.nc = im.nc;
+    };
 
     if (im.small_width) {
+        SlowCtx<ST> sc;
+        make_ctx(sc);
         slow_small_width<MODE, VARIANT, ST>(sc, ROWS, tid);
         return;
     }
@@ -582,14 +597,6 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     constexpr int NRU = ROWS / RPU;                                    // row groups per strip
     const int xunits = tw >> 3;
     const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && (MODE != MODE_HV || hv_avx);
-    if (!fast_ok) {
-        // SCALAR variant (i16 samples, unclamped DC-only values), odd strides, tiny 4:2:0 images: every sample
-        // takes the generic path, one sample per thread
-        for (int u = tid; u < ROWS * tw; u += ZJ_THREADS) {
-            const int yl = u / tw;
-            slow_pixel<MODE, VARIANT, ST>(sc, yl, u - yl * tw);
-        }
-    }
     // thread -> fixed x unit, loop over row groups: everything that depends only on the column is hoisted
     const int rpp = ZJ_THREADS / xunits;           // row groups per pass
     const int xu = tid % xunits, r0 = tid / xunits;
@@ -642,10 +649,7 @@ reconstruct_kernel(const DevImage *__restrict__ images)
             // edge unit: queue it; all threads share the queued samples after the loop (a warp that ran the
             // generic code inline would serialise ~10^4 instructions behind one or two active lanes)
             const int slot = atomicAdd(&sSlowN, 1);
-            if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)((rg << 8) | xu);
-            else {
-                for (int k = 0; k < 8; k++) { slow_pixel<MODE, VARIANT, ST>(sc, yl0, xl + k); if (RPU == 2) slow_pixel<MODE, VARIANT, ST>(sc, yl1, xl + k); }
-            }
+            if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)((rg << 8) | xu);  // (overflow: whole tile redone below)
             continue;
         }
         if constexpr (VARIANT == 0) {
@@ -721,17 +725,28 @@ reconstruct_kernel(const DevImage *__restrict__ images)
             }
         }
     }
-    if (fast_ok) {
-        __syncthreads();
-        const int nslow = min(sSlowN, ZJ_SLOW_CAP);
+    __syncthreads();
+    const int nslow = sSlowN;
+    if (!fast_ok || nslow > ZJ_SLOW_CAP) {
+        // SCALAR variant (i16 samples, unclamped DC-only values), odd strides, tiny 4:2:0 images (or a queue
+        // overflow): every sample takes the generic path, one sample per thread
+        SlowCtx<ST> sc;
+        make_ctx(sc);
+        for (int u = tid; u < ROWS * tw; u += ZJ_THREADS) {
+            const int yl = u / tw;
+            slow_pixel<MODE, VARIANT, ST>(sc, yl, u - yl * tw);
+        }
+    } else if (nslow > 0) {
+        SlowCtx<ST> sc;
+        make_ctx(sc);
         for (int t = tid; t < nslow * 8 * RPU; t += ZJ_THREADS) {
             const int e = sSlow[t / (8 * RPU)], r = (t >> 3) % RPU, k = t & 7;
-            const int rg = e >> 8, xl = (e & 0xff) << 3;
+            const int rg = e >> 8, xl2 = (e & 0xff) << 3;
             int yl;
             if (MODE == MODE_V) yl = 2 * rg + r;
             else if (MODE == MODE_HV) yl = 4 * (rg >> 1) + (rg & 1) + 2 * r;
             else yl = rg;
-            slow_pixel<MODE, VARIANT, ST>(sc, yl, xl + k);
+            slow_pixel<MODE, VARIANT, ST>(sc, yl, xl2 + k);
         }
     }
     // bytes of the row nobody writes: [P, stride) minus the tail chunk (Q5: 16 zero bytes; Q6: the w "alpha" bytes)
