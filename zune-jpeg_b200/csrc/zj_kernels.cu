@@ -641,8 +641,9 @@ reconstruct_kernel(const DevImage *__restrict__ images)
             const int p = rg & 1;
             l0 = (p * W + cc0) & 15;               // AVX2 lane of the unit's first sample
             hv_tail = p == 1 && cc0 + 4 > W - 16;  // last 32 outputs of an odd row: raw input shifted 17 samples left (Q4g)
-            // generic: the first vector of a double-row (stale lane-0 / lane-15 neighbours, Q4f; out[0] of far rows)
-            fast = fast && !(p == 0 && (cc0 == 0 || cc0 == 12)) && !(hv_tail && W - 36 < m0 * 8);
+            // generic only when the raw tail of a narrow last tile reaches outside it, or for images too narrow for the
+            // first-vector rule below
+            fast = fast && !(hv_tail && W - 36 < m0 * 8) && !(p == 0 && cc0 < 16 && W < 48);
         }
         if (nwords == 0 && fast) continue;         // nothing of this unit is ever written
         if (!fast) {
@@ -673,7 +674,7 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                 } else {
                     const int lc = 8 + (cc0 - m0 * 8);  // smem column of cc0 (multiple of 4)
                     // outer neighbours of the first / last unit of a row live one chroma row up / down (flat array)
-                    const int off0 = first_x ? -CS : 0, off2 = last_x ? CS : 0;
+                    const int off0 = (first_x && (MODE == MODE_H || (rg & 1))) ? -CS : 0, off2 = last_x ? CS : 0;
                     if (MODE == MODE_H) {
                         const uint8_t *pa = base + yl0 * CS + lc;
                         const u32 w0 = *reinterpret_cast<const u32 *>(pa - 4 + off0), w1 = *reinterpret_cast<const u32 *>(pa), w2 = *reinterpret_cast<const u32 *>(pa + 4 + off2);
@@ -704,12 +705,31 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                         // lane 15: the "next" value is the same expression on the next vector's first element
                         const u32 pv = (3u * ((Aa & 0xffffu) + (Ba & 0xffffu) + 2u)) >> 2;
                         const u32 pf = ((3u * ((Ah >> 16) + (Bh >> 16) + 2u)) >> 2) << 16;
+                        u32 pv2 = pv, pf2 = pf;
+                        if ((rg & 1) == 0 && cc0 < 16) {
+                            // first vector of a double-row (t = 0): its lane-0 / lane-15 neighbours are whatever the loop
+                            // left behind (upsampler/avx2.rs:67-68,264-270; Q4f): for j = 0 the raw in[0] / in[16], for
+                            // j >= 1 the values computed 16 samples before the end of double-row j-1 with ITS stride
+                            if (j == 0) {
+                                pv2 = Aa & 0xffffu;
+                                pf2 = Ah & 0xffff0000u;
+                            } else {
+                                const int spc0 = (m0 == 0 && nt > 1) ? 16 + tm * 8 : 8 + (W - 16 - m0 * 8);  // smem column of chroma col W-16
+                                const int rp = 2 * j - 1, rq = (j == 1) ? rp : rp + 2;                          // partner row: stride of double-row j-1
+                                const u32 x0 = base[rp * CS + spc0], x1 = base[rq * CS + spc0];
+                                pv2 = (3u * (x0 + x1 + 2u)) >> 2;
+                                const int c0s = 8 - m0 * 8;                                                     // smem column of chroma col 0 (tile 0)
+                                const u32 y0 = base[2 * j * CS + c0s], y1 = (j == 1) ? y0 : (j == 7 ? 0u : (u32)base[(2 * j + 2) * CS + c0s]);
+                                pf2 = ((3u * (y0 + y1 + 2u)) >> 2) << 16;
+                            }
+                        }
                         const u32 keep = (l0 == 0 ? 0xffff0000u : 0xffffffffu) & (l0 == 12 ? 0x0000ffffu : 0xffffffffu);
-                        const u32 ins = (l0 == 0 ? pv : 0u) | (l0 == 12 ? pf : 0u);
+                        const u32 ins = (l0 == 0 ? pv2 : 0u) | (l0 == 12 ? pf2 : 0u);
                         Nh = (Nh & keep) | ins;
                         Fh = (Fh & keep) | ins;
                         hfilter8(Nh, T2(Aa, Ba), T2(Ab, Bb), o0);
                         hfilter8(Fh, T2(Ba, Aa), T2(Bb, Ab), o1);
+                        if ((rg & 1) == 0 && cc0 == 0) o1[0] = (o1[0] >> 16) * 0x00010001u;  // far rows: out[0] = out[1] (avx2.rs:330)
                     }
                 }
             }
