@@ -52,6 +52,37 @@ __device__ __forceinline__ void idct8(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s
     s7 = (u32)((int)(x0 - d) >> SH);
 }
 
+
+// The same 1-D kernel with s4 = s5 = s6 = s7 = 0 folded in (identical results, fewer operations): used when a whole
+// warp's blocks have nothing outside the top-left 4x4 (99.8 % of the chroma blocks of a quality-90 photo).
+template <int SH>
+__device__ __forceinline__ void idct8_lo4(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s4, u32 &s5, u32 &s6, u32 &s7, const u32 bias)
+{
+    const u32 t2 = s2 * 2217u;                 // p1 + s6 * -7567 with s6 = 0
+    const u32 t3 = s2 * (2217u + 3135u);       // p1 + s2 * 3135
+    const u32 t0 = (s0 << 12) + bias;          // t0 == t1 when s4 = 0
+    const u32 x0 = t0 + t3, x3 = t0 - t3, x1 = t0 + t2, x2 = t0 - t2;
+    const u32 c = s3, d = s1;                  // a = s7 = 0, b = s5 = 0
+    const u32 p5 = (c + d) * 4816u;
+    const u32 q1 = p5 + d * (u32)(-3685);      // p1 = a + d = d
+    const u32 q2 = p5 + c * (u32)(-10497);     // p2 = b + c = c
+    const u32 p3 = c * (u32)(-8034);           // p3 = a + c = c
+    const u32 p4 = d * (u32)(-1597);           // p4 = b + d = d
+    const u32 dd = d * 6149u + q1 + p4, cc = c * 12586u + q2 + p3, bb = q2 + p4, aa = q1 + p3;
+    s0 = (u32)((int)(x0 + dd) >> SH);
+    s1 = (u32)((int)(x1 + cc) >> SH);
+    s2 = (u32)((int)(x2 + bb) >> SH);
+    s3 = (u32)((int)(x3 + aa) >> SH);
+    s4 = (u32)((int)(x3 - aa) >> SH);
+    s5 = (u32)((int)(x2 - bb) >> SH);
+    s6 = (u32)((int)(x1 - cc) >> SH);
+    s7 = (u32)((int)(x0 - dd) >> SH);
+}
+
+// x / n for 0 <= x, 1 <= n <= 1024 without an integer divide: (x + 0.5) / n is at least 0.5/n away from an integer,
+// far more than the error of the float reciprocal, so truncation is exact
+__device__ __forceinline__ int div_small(int x, float rcp_n) { return (int)(((float)x + 0.5f) * rcp_n); }
+
 __device__ __forceinline__ u32 clamp255(u32 v) { return (u32)max(min((int)v, 255), 0); }
 
 // s16x2 . u8 dot products (IDP.2A): unpack + dequantise one coefficient in a single instruction.
@@ -90,17 +121,28 @@ __device__ __forceinline__ void store_dc_row(int16_t *dst, const u32 v[8]) { sto
 //   VARIANT 0 (X86):    pass A along rows, pass B down columns, DC-only value clamped   (idct/avx2.rs:64-398)
 //   VARIANT 1 (SCALAR): pass A down columns, pass B along rows, DC-only value NOT clamped (idct/scalar.rs:19-282)
 // qtw: 32 words, word k = q[2k] | q[2k+1] << 24 (natural order).  dst rows must be 8 samples-aligned.
+// `active` lanes own a block; every lane of the warp must call this (warp votes pick the sparse code paths).
 template <int VARIANT, typename ST>
-__device__ __forceinline__ void idct_block(const int16_t *__restrict__ src, const u32 *__restrict__ qtw, ST *__restrict__ dst, int dst_stride)
+__device__ __forceinline__ void idct_block(const bool active, const int16_t *__restrict__ src, const u32 *__restrict__ qtw, ST *__restrict__ dst, int dst_stride)
 {
     const int4 *p = reinterpret_cast<const int4 *>(src);
     int4 raw[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) raw[r] = __ldg(p + r);
+    for (int r = 0; r < 8; r++) raw[r] = active ? __ldg(p + r) : make_int4(0, 0, 0, 0);
 
-    u32 acc = ((u32)raw[0].x & 0xffff0000u) | (u32)raw[0].y | (u32)raw[0].z | (u32)raw[0].w;
+    u32 rowor[8], col47 = 0;
+    rowor[0] = ((u32)raw[0].x & 0xffff0000u) | (u32)raw[0].y | (u32)raw[0].z | (u32)raw[0].w;
 #pragma unroll
-    for (int r = 1; r < 8; r++) acc |= (u32)raw[r].x | (u32)raw[r].y | (u32)raw[r].z | (u32)raw[r].w;
+    for (int r = 1; r < 8; r++) rowor[r] = (u32)raw[r].x | (u32)raw[r].y | (u32)raw[r].z | (u32)raw[r].w;
+#pragma unroll
+    for (int r = 0; r < 8; r++) col47 |= (u32)raw[r].z | (u32)raw[r].w;
+    const u32 r45 = rowor[4] | rowor[5], r67 = rowor[6] | rowor[7];
+    const u32 acc = rowor[0] | rowor[1] | rowor[2] | rowor[3] | r45 | r67;
+    // warp-uniform sparsity classes (a zero row / column transforms to exact zeros, so skipping it changes nothing)
+    const bool any_r67 = __any_sync(0xffffffffu, r67 != 0);
+    const bool any_r47 = __any_sync(0xffffffffu, (r45 | r67) != 0);
+    const bool any_c47 = __any_sync(0xffffffffu, col47 != 0);
+    if (!active) return;
 
     if (acc == 0) {
         // all 63 AC coefficients zero: ((c0 as i16).wrapping_mul(q0 as i16) >> 3) + 128 in i16
@@ -119,25 +161,55 @@ __device__ __forceinline__ void idct_block(const int16_t *__restrict__ src, cons
     }
 
     u32 a[64];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
+    const u32 SCALE_BITS = 512u + 65536u + (128u << 17);
+    auto dequant_row = [&](int r, int nwords) {
         const u32 w[4] = {(u32)raw[r].x, (u32)raw[r].y, (u32)raw[r].z, (u32)raw[r].w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            u32 q = qtw[r * 4 + k];
-            a[r * 8 + 2 * k] = dp2a_lo(w[k], q);
-            a[r * 8 + 2 * k + 1] = dp2a_hi(w[k], q);
+            if (k < nwords) {
+                const u32 q = qtw[r * 4 + k];
+                a[r * 8 + 2 * k] = dp2a_lo(w[k], q);
+                a[r * 8 + 2 * k + 1] = dp2a_hi(w[k], q);
+            } else {
+                a[r * 8 + 2 * k] = 0;
+                a[r * 8 + 2 * k + 1] = 0;
+            }
         }
-    }
-    const u32 SCALE_BITS = 512u + 65536u + (128u << 17);
+    };
     if (VARIANT == 0) {
+        if (!any_r47 && !any_c47) {
+            // top-left 4x4 only: 4 row transforms and 8 column transforms, each with 4 inputs
 #pragma unroll
-        for (int r = 0; r < 8; r++)
-            idct8<10>(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7], 512u);
+            for (int r = 0; r < 4; r++) {
+                dequant_row(r, 2);
+                idct8_lo4<10>(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7], 512u);
+            }
 #pragma unroll
-        for (int c = 0; c < 8; c++)
-            idct8<17>(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c], SCALE_BITS);
+            for (int c = 0; c < 8; c++)
+                idct8_lo4<17>(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c], SCALE_BITS);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                dequant_row(r, 4);
+                idct8<10>(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7], 512u);
+            }
+            if (any_r67) {
+#pragma unroll
+                for (int r = 6; r < 8; r++) {
+                    dequant_row(r, 4);
+                    idct8<10>(a[r * 8], a[r * 8 + 1], a[r * 8 + 2], a[r * 8 + 3], a[r * 8 + 4], a[r * 8 + 5], a[r * 8 + 6], a[r * 8 + 7], 512u);
+                }
+            } else {
+#pragma unroll
+                for (int k = 48; k < 64; k++) a[k] = 0;   // (0 * c + 512) >> 10 == 0
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                idct8<17>(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c], SCALE_BITS);
+        }
     } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) dequant_row(r, 4);
 #pragma unroll
         for (int c = 0; c < 8; c++)
             idct8<10>(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c], 512u);
@@ -489,6 +561,7 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     constexpr int TWC = 8 * MT::TM;           // chroma tile width
     constexpr int CS = TWC + 24;              // chroma smem row: halo | tile | halo | special
     static_assert(YROWS == ROWS, "luma rows");
+    static_assert(MT::YBR * MT::H * MT::TM + 2 * (MT::CBR * MT::TM + (MT::HALO ? 3 * MT::CBR : 0)) <= ZJ_THREADS, "one 8x8 block per thread");
 
     __shared__ __align__(16) ST sY[YROWS * TWY];
     __shared__ __align__(16) ST sC[2][CROWS * CS];
@@ -538,29 +611,34 @@ reconstruct_kernel(const DevImage *__restrict__ images)
         const int nHalo = MT::HALO ? MT::CBR : 0;     // per side per component
         const int nSp = spb >= 0 ? MT::CBR : 0;
         const int total = nY + 2 * (nC + 2 * nHalo + nSp);
-        for (int b = tid; b < total; b += ZJ_THREADS) {
-            const int16_t *src;
-            const u32 *qt;
-            ST *dst;
-            int dstride;
-            if (b < nY) {
-                const int br = b / (MT::H * tm), bc = b - br * (MT::H * tm);
+        const int per = nC + 2 * nHalo + nSp;
+        const float r_htm = __frcp_rn((float)(MT::H * tm)), r_tm = __frcp_rn((float)tm);
+        {
+            // total <= ZJ_THREADS (one block per thread); lanes without a block still take part in the warp votes
+            const int b = tid;
+            const bool active = b < total;
+            const int16_t *src = nullptr;
+            const u32 *qt = sQ[0];
+            ST *dst = sY;
+            int dstride = TWY;
+            if (!active) {
+            } else if (b < nY) {
+                const int br = div_small(b, r_htm), bc = b - br * (MT::H * tm);
                 const size_t blk = ((size_t)strip * MT::YBR + br) * ybpr + (size_t)MT::H * m0 + bc;
                 src = im.coeff[0] + blk * 64; qt = sQ[0]; dst = sY + br * 8 * TWY + bc * 8; dstride = TWY;
             } else {
                 int c = b - nY;
-                const int per = nC + 2 * nHalo + nSp;
-                const int comp = c / per;
+                const int comp = c >= per ? 1 : 0;
                 c -= comp * per;
                 int br, gcol, lcol;  // block row, global block column, smem column
-                if (c < nC) { br = c / tm; const int bc = c - br * tm; gcol = m0 + bc; lcol = 8 + bc * 8; }
+                if (c < nC) { br = div_small(c, r_tm); const int bc = c - br * tm; gcol = m0 + bc; lcol = 8 + bc * 8; }
                 else if (c < nC + nHalo) { br = c - nC; gcol = lhb; lcol = 0; }
                 else if (c < nC + 2 * nHalo) { br = c - nC - nHalo; gcol = rhb; lcol = 8 + tm * 8; }
                 else { br = c - nC - 2 * nHalo; gcol = spb; lcol = 16 + tm * 8; }
                 const size_t blk = ((size_t)strip * MT::CBR + br) * mcu_x + gcol;
                 src = im.coeff[1 + comp] + blk * 64; qt = sQ[1 + comp]; dst = sC[comp] + br * 8 * CS + lcol; dstride = CS;
             }
-            idct_block<VARIANT, ST>(src, qt, dst, dstride);  // the only call site: one copy of the unrolled IDCT
+            idct_block<VARIANT, ST>(active, src, qt, dst, dstride);  // the only call site: one copy of the unrolled IDCT
         }
     }
     __syncthreads();
@@ -598,8 +676,9 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     const int xunits = tw >> 3;
     const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && (MODE != MODE_HV || hv_avx);
     // thread -> fixed x unit, loop over row groups: everything that depends only on the column is hoisted
-    const int rpp = ZJ_THREADS / xunits;           // row groups per pass
-    const int xu = tid % xunits, r0 = tid / xunits;
+    const float r_xu = __frcp_rn((float)xunits);
+    const int rpp = div_small(ZJ_THREADS, r_xu);   // row groups per pass
+    const int r0 = div_small(tid, r_xu), xu = tid - r0 * xunits;
     const int xl = xu << 3;
     const int xs = X0 + xl;                        // first sample of the unit in the padded row
     const int cc0 = xs >> 1;                       // first chroma column (H, HV)
@@ -810,9 +889,10 @@ gray_kernel(const DevImage *__restrict__ images, int rows_per_strip)
     if (tid < 32) sQ[tid] = im.qtw[0][tid];
     __syncthreads();
     const int bc = blockIdx.x * ZJ_THREADS + tid;
-    if (bc >= ybpr) return;
-    const size_t blk = (size_t)br * ybpr + bc;
-    idct_block<VARIANT, ST>(im.coeff[0] + blk * 64, sQ, &sT[tid][0], 8);
+    const bool active = bc < ybpr;
+    const size_t blk = (size_t)br * ybpr + (active ? bc : 0);
+    idct_block<VARIANT, ST>(active, im.coeff[0] + blk * 64, sQ, &sT[tid][0], 8);
+    if (!active) return;
     const u32 x0 = (u32)bc * 8;
 #pragma unroll 1
     for (int r = 0; r < 8; r++) {
