@@ -345,8 +345,10 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
         if (rc) return rc;
     }
     cudaStream_t user = (cudaStream_t)stream;
-    constexpr int NS = 2;
-    cudaStream_t st[NS];
+    constexpr int NS_MAX = 4;
+    const char *env_ns = getenv("ZJ_E2E_STREAMS"), *env_mb = getenv("ZJ_E2E_BUDGET_MB");
+    const int NS = std::max(1, std::min(NS_MAX, env_ns ? atoi(env_ns) : 3));
+    cudaStream_t st[NS_MAX];
     for (int k = 0; k < NS; k++) CU(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
     // everything issued on `user` before this call must be visible
     cudaEvent_t ev_in;
@@ -354,7 +356,7 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
     CU(cudaEventRecord(ev_in, user));
     for (int k = 0; k < NS; k++) CU(cudaStreamWaitEvent(st[k], ev_in, 0));
 
-    const size_t budget = (size_t)1 << 30;  // ~1 GiB of device staging per sub-batch
+    const size_t budget = (size_t)(env_mb ? std::max(16, atoi(env_mb)) : 256) << 20;  // device staging per sub-batch
     std::vector<void *> to_free;
     std::vector<zj_batch *> batches;
     size_t i = 0;
