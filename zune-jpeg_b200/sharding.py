@@ -42,7 +42,10 @@ class Plumbing:
                 torch.cuda.set_device(self.local_rank)
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29531")
-            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = torch.device(f"cuda:{self.local_rank}")
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world, **kw)
             self.dist, self.torch, self.backend = dist, torch, backend
 
     def _tensor(self, v):
