@@ -121,14 +121,18 @@ __device__ __forceinline__ void store_dc_row(int16_t *dst, const u32 v[8]) { sto
 //   VARIANT 0 (X86):    pass A along rows, pass B down columns, DC-only value clamped   (idct/avx2.rs:64-398)
 //   VARIANT 1 (SCALAR): pass A down columns, pass B along rows, DC-only value NOT clamped (idct/scalar.rs:19-282)
 // qtw: 32 words, word k = q[2k] | q[2k+1] << 24 (natural order).  dst rows must be 8 samples-aligned.
-// `active` lanes own a block; every lane of the warp must call this (warp votes pick the sparse code paths).
-template <int VARIANT, typename ST>
-__device__ __forceinline__ void idct_block(const bool active, const int16_t *__restrict__ src, const u32 *__restrict__ qtw, ST *__restrict__ dst, int dst_stride)
+// 128-bit loads of one block's 64 coefficients (read once: non-coherent path); lanes without a block get zeros
+__device__ __forceinline__ void load_block(const bool active, const int16_t *__restrict__ src, int4 (&raw)[8])
 {
     const int4 *p = reinterpret_cast<const int4 *>(src);
-    int4 raw[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) raw[r] = active ? __ldg(p + r) : make_int4(0, 0, 0, 0);
+}
+
+// `active` lanes own a block; every lane of the warp must call this (warp votes pick the sparse code paths).
+template <int VARIANT, typename ST>
+__device__ __forceinline__ void idct_block(const bool active, const int4 (&raw)[8], const u32 *__restrict__ qtw, ST *__restrict__ dst, int dst_stride)
+{
 
     u32 rowor[8], col47 = 0;
     rowor[0] = ((u32)raw[0].x & 0xffff0000u) | (u32)raw[0].y | (u32)raw[0].z | (u32)raw[0].w;
@@ -595,10 +599,6 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     const int Wp = (int)im.Wp, W = (int)im.W;
     const int ybpr = MT::H * mcu_x;              // luma blocks per block-row of the plane
 
-    for (int k = tid; k < 96; k += ZJ_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
-    if (tid == 0) sSlowN = 0;
-    __syncthreads();
-
     // ---------------------------------------------------------------- phase 1: IDCT into shared planes
     const int lhb = (MT::HALO && mcu_x > 0) ? (m0 == 0 ? mcu_x - 1 : m0 - 1) : -1;  // wraps: flat filters cross row ends
     const int rhb = MT::HALO ? (m1 == mcu_x ? 0 : m1) : -1;
@@ -638,7 +638,13 @@ reconstruct_kernel(const DevImage *__restrict__ images)
                 const size_t blk = ((size_t)strip * MT::CBR + br) * mcu_x + gcol;
                 src = im.coeff[1 + comp] + blk * 64; qt = sQ[1 + comp]; dst = sC[comp] + br * 8 * CS + lcol; dstride = CS;
             }
-            idct_block<VARIANT, ST>(active, src, qt, dst, dstride);  // the only call site: one copy of the unrolled IDCT
+            // issue the coefficient loads first; the table copy and the barrier below overlap their latency
+            int4 raw[8];
+            load_block(active, src, raw);
+            for (int k = tid; k < 96; k += ZJ_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
+            if (tid == 0) sSlowN = 0;
+            __syncthreads();
+            idct_block<VARIANT, ST>(active, raw, qt, dst, dstride);  // the only call site: one copy of the unrolled IDCT
         }
     }
     __syncthreads();
@@ -891,7 +897,9 @@ gray_kernel(const DevImage *__restrict__ images, int rows_per_strip)
     const int bc = blockIdx.x * ZJ_THREADS + tid;
     const bool active = bc < ybpr;
     const size_t blk = (size_t)br * ybpr + (active ? bc : 0);
-    idct_block<VARIANT, ST>(active, im.coeff[0] + blk * 64, sQ, &sT[tid][0], 8);
+    int4 raw[8];
+    load_block(active, im.coeff[0] + blk * 64, raw);
+    idct_block<VARIANT, ST>(active, raw, sQ, &sT[tid][0], 8);
     if (!active) return;
     const u32 x0 = (u32)bc * 8;
 #pragma unroll 1
