@@ -44,7 +44,7 @@ static int num_components(uint32_t cs)  // ColorSpace::num_components, reference
 
 // --------------------------------------------------------------------------------------------- planning
 struct Plan {
-    int mode, variant, gray, zero_only;
+    int mode, variant, gray, zero_only, fast;
     uint32_t n_strips, rows, ncomp_used;
     size_t chunk[3];   // i16 per strip per component
     size_t out_size;
@@ -54,7 +54,7 @@ struct Plan {
 
 // Strip geometry of reference src/mcu.rs:139-226 (baseline) / src/mcu_prog.rs:132-203 (progressive) and the
 // colour-writer constants of src/worker.rs:143-251.
-static int plan_image(const zj_image *img, Plan *pl)
+static int plan_image(const zj_image *img, Plan *pl, const void *out = nullptr)
 {
     if (!img) return ZJ_ERR_INVALID_ARG;
     if (img->n_comp != 1 && img->n_comp != 3) return ZJ_ERR_INVALID_ARG;
@@ -155,11 +155,22 @@ static int plan_image(const zj_image *img, Plan *pl)
         }
     }
     if (kind != OUT_GRAY) {
-        const int tmv[4] = {TM_NONE, TM_H, TM_V, TM_HV};
-        d.n_tiles = (mcu_x + tmv[mode] - 1) / tmv[mode];
+        // the fast kernel covers the X86 variant with word-aligned rows; everything else runs the generic kernel
+        pl->fast = img->variant == ZJ_VARIANT_X86 && (kind == OUT_RGB || kind == OUT_YCC) && !d.small_width && (d.stride & 3u) == 0 &&
+                   (mode != MODE_HV || d.hv_avx) && (reinterpret_cast<uintptr_t>(out) & 3) == 0 && !getenv("ZJ_NO_FAST");
+        if (pl->fast) {
+            const uint32_t xuv[4] = {ZF_XU_NONE, ZF_XU_H, ZF_XU_V, ZF_XU_HV};
+            const uint32_t ucols = (d.Wp + 15) / 16;            // 16-sample unit columns
+            d.n_tiles = (ucols + xuv[mode] - 1) / xuv[mode];
+            d.tile_q = ucols / d.n_tiles;
+            d.tile_r = ucols % d.n_tiles;
+        } else {
+            const int tmv[4] = {TM_NONE, TM_H, TM_V, TM_HV};
+            d.n_tiles = (mcu_x + tmv[mode] - 1) / tmv[mode];
+            d.tile_q = mcu_x / d.n_tiles;
+            d.tile_r = mcu_x % d.n_tiles;
+        }
         pl->grid_tiles = d.n_tiles;
-        d.tile_q = mcu_x / d.n_tiles;
-        d.tile_r = mcu_x % d.n_tiles;
         d.magic_w = d.W ? (((uint64_t)1 << 40) + d.W - 1) / d.W : 0;
     }
     return ZJ_OK;
@@ -245,7 +256,7 @@ int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *
     if (rc) return rc;
     std::vector<Plan> plans(n);
     for (size_t i = 0; i < n; i++) {
-        rc = plan_image(&imgs[i], &plans[i]);
+        rc = plan_image(&imgs[i], &plans[i], out_dev[i]);
         if (rc) return rc;
         rc = check_buffers(&imgs[i], plans[i], out_dev[i], out_len[i]);
         if (rc) return rc;
@@ -265,14 +276,14 @@ int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *
         b->algo_bytes += plans[i].out_size;
         for (uint32_t z = 0; z < plans[i].ncomp_used; z++) b->algo_bytes += (uint64_t)plans[i].n_strips * plans[i].chunk[z] * 2;
     }
-    auto key = [&](size_t i) { return plans[i].gray * 16 + plans[i].mode * 2 + plans[i].variant; };
+    auto key = [&](size_t i) { return plans[i].gray * 32 + plans[i].fast * 16 + plans[i].mode * 2 + plans[i].variant; };
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t c) { return key(a) < key(c); });
     std::vector<DevImage> host(order.size());
     for (size_t k = 0; k < order.size(); k++) host[k] = plans[order[k]].dev;
     for (size_t k = 0; k < order.size();) {
         size_t e = k;
         LaunchGroup g{};
-        g.gray = plans[order[k]].gray; g.mode = plans[order[k]].mode; g.variant = plans[order[k]].variant;
+        g.gray = plans[order[k]].gray; g.mode = plans[order[k]].mode; g.variant = plans[order[k]].variant; g.fast = plans[order[k]].fast;
         g.first = (uint32_t)k;
         while (e < order.size() && key(order[e]) == key(order[k]) && e - k < 65535) {
             g.max_tiles = std::max(g.max_tiles, plans[order[e]].grid_tiles);

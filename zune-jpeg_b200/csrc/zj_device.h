@@ -32,6 +32,19 @@ constexpr int ZJ_SLOW_CAP = 192;  // edge units per tile queued for the generic 
 // tile widths scale with the CTA size (128 threads: 40 / 15 / 32 / 10)
 constexpr int TM_NONE = 40 * ZJ_THREADS / 128, TM_H = 15 * ZJ_THREADS / 128, TM_V = 32 * ZJ_THREADS / 128, TM_HV = 10 * ZJ_THREADS / 128, TM_GRAY = 128;
 
+// The fast kernel (X86 variant): 256 threads, every thread owns one 8x8 block and one 16-sample unit per strip.
+#ifndef ZF_CFG_MINBLOCKS
+#define ZF_CFG_MINBLOCKS 3
+#endif
+#ifndef ZF_CFG_SPC
+#define ZF_CFG_SPC 4
+#endif
+constexpr int ZF_THREADS = 256;
+constexpr int ZF_MINBLOCKS = ZF_CFG_MINBLOCKS;
+constexpr int ZF_DEFAULT_SPC = ZF_CFG_SPC;      // strips per CTA
+// unit columns (16 luma samples) per tile: ZF_THREADS / row groups per strip
+constexpr int ZF_XU_NONE = ZF_THREADS / 8, ZF_XU_H = ZF_THREADS / 16, ZF_XU_V = ZF_THREADS / 8, ZF_XU_HV = ZF_THREADS / 16;
+
 struct DevImage {
     const int16_t *coeff[3];  // device pointers, whole-image planes
     uint8_t *out;             // device pointer, width*height*nc bytes
@@ -52,13 +65,14 @@ struct DevImage {
     uint32_t small_width;     // width < 16: temp-buffer path (worker.rs:158-163,176-198)
     uint32_t hv_avx;          // HV + X86 + chroma strip >= 500 samples -> AVX2 closed form
     uint32_t gray_rows_ok;    // Q7 resolved: 1 = plain row copy is what the reference does
-    uint32_t tile_q, tile_r;  // tile t covers MCU columns [t*q + min(t,r), ...): the first r tiles are one column wider
+    uint32_t tile_q, tile_r;  // tile t covers MCU columns (fast kernel: 16-sample unit columns) [t*q + min(t,r), ...): the first r tiles are one wider
     uint64_t magic_w;         // ceil(2^40 / W): idx / W == (idx * magic_w) >> 40 for idx < 2^20
 };
 
 // Host-side launch plan entry: one kernel launch per (mode, variant, out-kind class) group.
 struct LaunchGroup {
     int mode, variant, gray;  // gray = luma-only kernel
+    int fast;                 // reconstruct_fast_kernel (X86 variant, aligned output)
     uint32_t first, count;    // images [first, first+count) of the sorted device array
     uint32_t max_tiles, max_strips;
 };

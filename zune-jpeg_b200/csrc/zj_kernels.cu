@@ -12,6 +12,7 @@
 // Everything is integer and must be bit-exact against oracle/ (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -865,6 +866,395 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     }
 }
 
+// =========================================================================== the fast kernel (X86 variant)
+// Same arithmetic as above, organised so that nothing is decided twice: a CTA of 256 threads owns one tile column
+// of `spc` consecutive strips; in every strip each thread transforms (at most) ONE 8x8 block and then produces ONE
+// unit = 16 luma columns (one conv16 chunk of the reference, color_convert/avx.rs:67-107) of one output row
+// (NONE, H) or of the two rows that share their chroma inputs (V, HV).  Everything that depends only on the
+// thread's position in the tile -- block pointers, the row writer's placement rule, the AVX2 lane of the unit,
+// neighbour offsets -- is computed once, before the strip loop.  Units the packed code does not cover are queued
+// once and handled per sample by the generic path (slow_pixel) in every strip.
+template <int MODE> struct FastTraits {
+    static constexpr int H = (MODE == MODE_H || MODE == MODE_HV) ? 2 : 1, V = (MODE == MODE_V || MODE == MODE_HV) ? 2 : 1;
+    static constexpr int ROWS = 8 * H * V;            // output rows per strip (mcu.rs:226)
+    static constexpr int YBR = H * V, CBR = H;        // block rows per strip: luma / chroma
+    static constexpr int CROWS = 8 * CBR;
+    static constexpr int RPU = V;                     // rows per unit
+    static constexpr int NRG = ROWS / RPU;            // row groups per strip
+    static constexpr int XU = ZF_THREADS / NRG;       // unit columns per tile
+    static constexpr int TWY = 16 * XU;               // luma samples per tile row
+    static constexpr int TWC = TWY / H;               // chroma samples per tile row
+    static constexpr int YB = TWY / 8, CB = TWC / 8;  // blocks per block row of the tile
+    static constexpr int CS = TWC + 24;               // chroma smem row: left halo | tile | right halo | special
+    static constexpr int NSLOT = MODE == MODE_H ? 2 : (MODE == MODE_HV ? 3 : 0);  // halo block columns per chroma plane
+    static constexpr int NY = YBR * YB, NC = CBR * CB, PER = NC + NSLOT * CBR;
+    static_assert(NY + 2 * PER <= ZF_THREADS, "one 8x8 block per thread");
+};
+
+__device__ __forceinline__ u32 evens(u32 w) { return prmt(w, 0u, 0x4240u); }  // bytes 0,2 -> 16-bit lanes
+__device__ __forceinline__ u32 odds(u32 w) { return prmt(w, 0u, 0x4341u); }   // bytes 1,3 -> 16-bit lanes
+
+// Horizontal x2 triangle filter of eight samples R0..R7 (r[k] = (R2k, R2k+1) as lane pairs) with outer neighbours
+// h = (R(-1), R8):  out[2i] = T(R[i], R[i-1]), out[2i+1] = T(R[i], R[i+1])  (upsampler/scalar.rs:30-42 == avx2.rs:178-197)
+// Results as E[k] = (out[4k], out[4k+2]), O[k] = (out[4k+1], out[4k+3]); lanes are 9 bits wide because a mis-scaled
+// lane-0/15 neighbour (Q4e) can push a result to 287.
+__device__ __forceinline__ void hfilter16(u32 h, const u32 r[4], u32 E[4], u32 O[4])
+{
+    u32 L[5];
+    L[0] = prmt(h, r[0], 0x5410u);       // (R(-1), R0)
+    L[1] = prmt(r[0], r[1], 0x5432u);    // (R1, R2)
+    L[2] = prmt(r[1], r[2], 0x5432u);
+    L[3] = prmt(r[2], r[3], 0x5432u);
+    L[4] = prmt(r[3], h, 0x7632u);       // (R7, R8)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 p3 = r[k] * 3u + 0x00020002u;
+        E[k] = ((p3 + L[k]) >> 2) & 0x01ff01ffu;
+        O[k] = ((p3 + L[k + 1]) >> 2) & 0x01ff01ffu;
+    }
+}
+
+// 16 pixels of one row -> 48 interleaved bytes.  yw: the 16 luma bytes; cbE/cbO/crE/crO: chroma in the E/O
+// arrangement of hfilter16.  nw = number of leading 32-bit words to store (12, or fewer when the row's tail chunk
+// overwrites the rest, worker.rs:221-246); vec = 16-byte stores are aligned.
+__device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 cbE[4], const u32 cbO[4], const u32 crE[4], const u32 crO[4],
+                                       const bool ycc, const int nw, const bool vec)
+{
+    u32 w[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 yE = evens(yw[k]), yO = odds(yw[k]);
+        u32 c0E, c1E, c2E, c0O, c1O, c2O;
+        if (ycc) {  // `as u8` interleave (color_convert/scalar.rs:152-161)
+            c0E = yE; c1E = cbE[k]; c2E = crE[k]; c0O = yO; c1O = cbO[k]; c2O = crO[k];
+        } else {
+            convert_pair(yE, cbE[k], crE[k], c0E, c1E, c2E);
+            convert_pair(yO, cbO[k], crO[k], c0O, c1O, c2O);
+        }
+        const u32 rgE = prmt(c0E, c1E, 0x6240u);   // [R0 G0 R2 G2]
+        const u32 brO = prmt(c2E, c0O, 0x6240u);   // [B0 R1 B2 R3]
+        const u32 gbO = prmt(c1O, c2O, 0x6240u);   // [G1 B1 G3 B3]
+        w[3 * k] = prmt(rgE, brO, 0x5410u);        // [R0 G0 B0 R1]
+        w[3 * k + 1] = prmt(gbO, rgE, 0x7610u);    // [G1 B1 R2 G2]
+        w[3 * k + 2] = prmt(brO, gbO, 0x7632u);    // [B2 R3 G3 B3]
+    }
+    if (vec && nw == 12) {
+        uint4 *d = reinterpret_cast<uint4 *>(dst);
+        d[0] = make_uint4(w[0], w[1], w[2], w[3]); d[1] = make_uint4(w[4], w[5], w[6], w[7]); d[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    } else if (vec && nw == 8) {
+        uint4 *d = reinterpret_cast<uint4 *>(dst);
+        d[0] = make_uint4(w[0], w[1], w[2], w[3]); d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+        u32 *d = reinterpret_cast<u32 *>(dst);
+#pragma unroll
+        for (int k = 0; k < 12; k++) if (k < nw) d[k] = w[k];
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ZF_THREADS, ZF_MINBLOCKS)
+reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
+{
+    typedef FastTraits<MODE> FT;
+    typedef uint8_t ST;
+    constexpr int ROWS = FT::ROWS, TWY = FT::TWY, CS = FT::CS, NRG = FT::NRG, XU = FT::XU, RPU = FT::RPU;
+    constexpr bool HALO = FT::NSLOT > 0;
+
+    __shared__ __align__(16) ST sY[ROWS * TWY];
+    __shared__ __align__(16) ST sC[2][FT::CROWS * CS];
+    __shared__ u32 sQ[3][32];
+    __shared__ int sSlowN;
+    __shared__ unsigned short sSlow[ZJ_SLOW_CAP];  // units left to the generic path (row group << 8 | tile column / 8)
+
+    const DevImage &im = images[blockIdx.z];
+    const u32 tile = blockIdx.x;
+    if (tile >= im.n_tiles) return;
+    const int tid = threadIdx.x;
+    const u32 stride = im.stride;
+    uint8_t *__restrict__ out = im.out;
+    const u32 n_strips = im.n_strips;
+    const u32 s_begin = blockIdx.y * (u32)spc;
+
+    // rows below the last processed strip stay zero in the reference (Q1 dropped MCU row, mcu.rs:154,158):
+    // written by the first row of CTAs past the image's strips
+    if (s_begin >= n_strips) {
+        if (s_begin >= n_strips + (u32)spc) return;
+        const size_t lo = (size_t)n_strips * ROWS * stride, hi = (size_t)im.height * stride;
+        if (lo >= hi) return;
+        const size_t span = hi - lo, per = (span + im.n_tiles - 1) / im.n_tiles;
+        size_t b0 = lo + (size_t)tile * per, b1 = b0 + per;
+        if (b1 > hi) b1 = hi;
+        for (size_t b = b0 + tid; b < b1; b += ZF_THREADS) out[b] = 0;
+        return;
+    }
+    const u32 s_end = min(s_begin + (u32)spc, n_strips);
+
+    // tile -> unit columns [u0, u1) (16 luma samples each), spread evenly: the first tile_r tiles are one wider
+    const int nt = (int)im.n_tiles;
+    const int u0 = (int)(tile * im.tile_q + min(tile, im.tile_r)), u1 = (int)((tile + 1) * im.tile_q + min(tile + 1, im.tile_r));
+    const int Wp = (int)im.Wp, W = (int)im.W, mcu_x = (int)im.mcu_x;
+    const int X0 = 16 * u0;                                        // first luma column of the tile
+    const int yb0 = 2 * u0, nyb = min(2 * u1, Wp >> 3) - yb0;      // luma block columns of the tile
+    const int cb0 = FT::H == 2 ? u0 : yb0, ncb = FT::H == 2 ? u1 - u0 : nyb;  // chroma block columns
+    const bool last_tile = (tile + 1 == (u32)nt);
+    // halo block columns wrap around the image: the flat filters run across row ends (Q4a); tile 0 of the AVX2 HV
+    // form also needs block column mcu_x-2 for the stale first-vector neighbours (Q4f)
+    const int lhb = HALO ? (cb0 == 0 ? mcu_x - 1 : cb0 - 1) : -1;
+    const int rhb = HALO ? (cb0 + ncb == mcu_x ? 0 : cb0 + ncb) : -1;
+    const int spb = (MODE == MODE_HV && tile == 0 && nt > 1) ? mcu_x - 2 : -1;
+
+    // ------------------------------------------------------------ per-thread block of phase 1 (strip-invariant)
+    bool active;
+    const int16_t *src;
+    size_t src_step;          // i16 per strip
+    const u32 *qt;
+    ST *dst;
+    int dstride;
+    if (tid < FT::NY) {
+        const int br = tid / FT::YB, bc = tid % FT::YB;
+        active = bc < nyb;
+        const int ybpr = Wp >> 3;
+        src_step = (size_t)FT::YBR * ybpr * 64;
+        src = im.coeff[0] + (((size_t)s_begin * FT::YBR + br) * ybpr + yb0 + bc) * 64;
+        qt = sQ[0]; dst = sY + br * 8 * TWY + bc * 8; dstride = TWY;
+    } else {
+        int c = tid - FT::NY;
+        const int comp = c >= FT::PER ? 1 : 0;
+        c -= comp * FT::PER;
+        int br, gcol, lcol;
+        if (c < FT::NC) { br = c / FT::CB; const int bc = c % FT::CB; gcol = bc < ncb ? cb0 + bc : -1; lcol = 8 + bc * 8; }
+        else {
+            const int hi = c - FT::NC, slot = hi / FT::CBR;
+            br = hi % FT::CBR;
+            gcol = slot == 0 ? lhb : (slot == 1 ? rhb : spb);
+            lcol = slot == 0 ? 0 : (slot == 1 ? 8 + ncb * 8 : 16 + ncb * 8);
+            if (slot >= FT::NSLOT) gcol = -1;
+        }
+        active = comp < 2 && c < FT::PER && gcol >= 0;
+        src_step = (size_t)FT::CBR * mcu_x * 64;
+        src = im.coeff[1 + comp] + (((size_t)s_begin * FT::CBR + br) * mcu_x + (active ? gcol : 0)) * 64;
+        qt = sQ[1 + comp]; dst = sC[comp] + br * 8 * CS + lcol; dstride = CS;
+    }
+    if (!active) src = im.coeff[0];
+
+    // ------------------------------------------------------------ per-thread unit of phase 2 (strip-invariant)
+    const int xu = tid % XU, rg = tid / XU;
+    const u32 n_norm = im.n_norm, T = im.T, P = im.P;
+    const bool ycc = im.out_kind == OUT_YCC;
+    int xs = X0 + 16 * xu;                          // first sample of the unit in the padded row
+    // Where the unit's 48 bytes go (worker.rs:201-246): samples < n_norm ("normal" 16-sample chunks) sit at
+    // byte 3*s, except bytes the tail chunk overwrites; the tail chunk (samples Wp-16..Wp-1) sits at T; the rest is never written
+    int kind = 0;                                   // 0 = nothing to write, 1 = packed path, 2 = generic path
+    int dst_off = 3 * xs, nw = 12;
+    if (u0 + xu < u1) {
+        if ((u32)(xs + 16) <= n_norm) {
+            kind = 1;
+            if (T != 0xffffffffu && (u32)(3 * xs + 48) > T && (u32)(3 * xs) < T + 48) {   // overlaps the tail chunk's bytes [T, T+48)
+                const int keep = (int)T - 3 * xs;                                        // bytes before T survive
+                if ((u32)(3 * xs + 48) > T + 48) kind = 2;
+                else if (keep <= 0) kind = 0;
+                else if ((keep & 3) == 0) nw = keep >> 2;
+                else kind = 2;
+            }
+        } else if (T != 0xffffffffu && (u0 + xu) == ((Wp - 16) >> 4)) {
+            kind = 1; xs = Wp - 16; dst_off = (int)T;
+        } else if ((u32)xs < n_norm) {
+            kind = 2;                                                                     // partially inside [0, n_norm): YCbCr output, width % 16 != 0
+        }
+    }
+    if (kind == 1 && (dst_off & 3) != 0) kind = 2;
+    const bool vec = ((stride & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((dst_off & 15) == 0) && ((nw & 3) == 0);
+    const int xl = xs - X0;                          // tile-local luma column
+    // rows of the unit inside the strip
+    int yl0, yl1;
+    if (MODE == MODE_V) { yl0 = 2 * rg; yl1 = yl0 + 1; }
+    else if (MODE == MODE_HV) { yl0 = 4 * (rg >> 1) + (rg & 1); yl1 = yl0 + 2; }
+    else { yl0 = rg; yl1 = rg; }
+    // chroma geometry of the unit
+    const int cc0 = FT::H == 2 ? xs >> 1 : xs;       // first chroma column
+    const int lc = 8 + (cc0 - cb0 * 8);              // its smem column
+    const bool first_x = HALO && cc0 == 0, last_x = HALO && cc0 + 8 == W;
+    int ra = 0, rb = 0, off0 = 0, off2 = 0;          // chroma rows blended (V, HV) and neighbour row offsets (flat filters)
+    bool sel0 = false, firstvec = false, hv_tail = false;
+    if (MODE == MODE_V) {
+        ra = rg == 0 ? 0 : (rg == 7 ? 7 : rg); rb = rg == 0 ? 0 : (rg == 7 ? 7 : rg + 1);   // scalar.rs:64-147 (Q4c)
+    } else if (MODE == MODE_H) {
+        ra = rg;
+        off0 = first_x ? -CS : 0; off2 = last_x ? CS : 0;
+        // strip start (out[0], out[1] edge rule) and strip end (scalar.rs:46-57 / the SSE tail Q4b) stay generic
+        if (kind == 1 && ((first_x && rg == 0) || (last_x && rg == NRG - 1))) kind = 2;
+    } else if (MODE == MODE_HV) {
+        const int j = rg >> 1, p = rg & 1;
+        ra = 2 * j + p; rb = (j == 0 || j == 7) ? ra : ra + 2;       // double-row j blends chroma rows 2j+p and 2j+p+2 (Q4d)
+        off0 = (first_x && p) ? -CS : 0; off2 = last_x ? CS : 0;
+        sel0 = (((p ? W : 0) + cc0) & 15) == 0;                        // unit starts an AVX2 vector (else it ends one)
+        firstvec = p == 0 && cc0 < 16;                                 // vector t = 0 of the double-row (Q4f)
+        hv_tail = p == 1 && cc0 + 16 >= W;                             // last 32 outputs of the double-row (Q4g)
+        if (kind == 1 && hv_tail && W - 36 - cb0 * 8 < (cb0 == 0 ? 0 : -8)) kind = 2;  // raw tail reaches left of the tile's halo (or wraps a row)
+        if (kind == 1 && firstvec && W < 48) kind = 2;
+    }
+
+    for (int k = tid; k < 96; k += ZF_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
+    if (tid == 0) sSlowN = 0;
+    __syncthreads();
+    if (kind == 2) {
+        const int slot = atomicAdd(&sSlowN, 1);
+        if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)((rg << 8) | (xl >> 3));
+    }
+    __syncthreads();
+    const int nslow = sSlowN;
+
+    const uint8_t *const yrow0 = sY + yl0 * TWY + xl, *const yrow1 = sY + yl1 * TWY + xl;
+    // bytes of a row nobody writes: [P, stride) minus the tail chunk [T, T+48) (Q5: 16 zero bytes; Q6: the w "alpha"
+    // bytes) = [z0, stride); every tile zeroes its share, with the widest stores the alignment allows
+    const u32 z0 = (T != 0xffffffffu && T + 48 > P) ? T + 48 : P;
+    const u32 zlen = stride > z0 ? stride - z0 : 0;
+    const int zg = (((z0 | stride) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 16 : ((((z0 | stride) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) ? 4 : 1);
+    const u32 zper = ((zlen / zg + nt - 1) / nt) * zg;             // bytes per tile (multiple of the store size)
+    const u32 zb0 = min(z0 + tile * zper, stride), zb1 = min(zb0 + zper, stride);
+    const int zcnt = (int)((zb1 - zb0) / zg);                     // stores per row for this tile
+
+    for (u32 strip = s_begin; strip < s_end; strip++) {
+        // ------------------------------------------------------------ phase 1: IDCT into the shared planes
+        int4 raw[8];
+        load_block(active, src, raw);
+        src += src_step;
+        if (strip != s_begin) __syncthreads();         // the previous strip's readers are done with the planes
+        idct_block<0, ST>(active, raw, qt, dst, dstride);
+        __syncthreads();
+
+        // ------------------------------------------------------------ phase 2: up-sample, convert, write
+        const u32 y_base = strip * ROWS;
+        if (kind == 1) {
+            u32 E0[2][4], O0[2][4], E1[2][4], O1[2][4];   // [cb|cr] chroma of row 0 / row 1 of the unit, E/O arrangement
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint8_t *base = sC[c];
+                if (MODE == MODE_NONE) {
+                    const uint2 v0 = *reinterpret_cast<const uint2 *>(base + yl0 * CS + lc), v1 = *reinterpret_cast<const uint2 *>(base + yl0 * CS + lc + 8);
+                    const u32 w[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { E0[c][k] = evens(w[k]); O0[c][k] = odds(w[k]); }
+                } else if (MODE == MODE_V) {
+                    const uint2 a0 = *reinterpret_cast<const uint2 *>(base + ra * CS + lc), a1 = *reinterpret_cast<const uint2 *>(base + ra * CS + lc + 8);
+                    const uint2 b0 = *reinterpret_cast<const uint2 *>(base + rb * CS + lc), b1 = *reinterpret_cast<const uint2 *>(base + rb * CS + lc + 8);
+                    const u32 a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const u32 aE = evens(a[k]), aO = odds(a[k]), bE = evens(b[k]), bO = odds(b[k]);
+                        E0[c][k] = T2(aE, bE); O0[c][k] = T2(aO, bO);      // rows 2k, 2k+1 <- T(r_k, r_k+1), T(r_k+1, r_k)
+                        E1[c][k] = T2(bE, aE); O1[c][k] = T2(bO, aO);
+                    }
+                } else if (MODE == MODE_H) {
+                    const uint8_t *pa = base + ra * CS + lc;
+                    const uint2 a = *reinterpret_cast<const uint2 *>(pa);
+                    const u32 h = (u32)pa[off0 - 1] | ((u32)pa[off2 + 8] << 16);
+                    const u32 r[4] = {lanes01(a.x), lanes23(a.x), lanes01(a.y), lanes23(a.y)};
+                    hfilter16(h, r, E0[c], O0[c]);
+                } else if (!hv_tail) {
+                    const uint8_t *pa = base + ra * CS + lc, *pb = base + rb * CS + lc;
+                    const uint2 a = *reinterpret_cast<const uint2 *>(pa), b = *reinterpret_cast<const uint2 *>(pb);
+                    const u32 aL = pa[off0 - 1], aR = pa[off2 + 8], bL = pb[off0 - 1], bR = pb[off2 + 8];
+                    const u32 A[4] = {lanes01(a.x), lanes23(a.x), lanes01(a.y), lanes23(a.y)};
+                    const u32 B[4] = {lanes01(b.x), lanes23(b.x), lanes01(b.y), lanes23(b.y)};
+                    const u32 Ah = aL | (aR << 16), Bh = bL | (bR << 16);
+                    u32 N[4], F[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { N[k] = T2(A[k], B[k]); F[k] = T2(B[k], A[k]); }
+                    u32 Nh = T2(Ah, Bh), Fh = T2(Bh, Ah);
+                    // AVX2 form: lane 0 of a vector takes 3*(in+in'+2)>>2 of its OWN first element as "previous" value,
+                    // lane 15 the same expression of the next vector's first element as "next" value (Q4e)
+                    u32 pv = (3u * ((sel0 ? (a.x & 0xffu) + (b.x & 0xffu) : aR + bR) + 2u)) >> 2;
+                    if (firstvec) {
+                        // vector t = 0: the neighbours are whatever the loop left behind (avx2.rs:67-68,264-270; Q4f): for
+                        // j = 0 the raw in[0] / in[16], for j >= 1 the values computed 16 samples before the end of
+                        // double-row j-1 (lane 0) and at the start of double-row j (lane 15), both with the stride of j-1
+                        const int j = rg >> 1;
+                        if (j == 0) pv = sel0 ? (a.x & 0xffu) : aR;
+                        else if (sel0) {
+                            const int spc0 = nt > 1 ? 16 + ncb * 8 : 8 + (W - 16);                 // smem column of chroma column W-16
+                            const int rp = 2 * j - 1, rq = (j == 1) ? rp : rp + 2;
+                            pv = (3u * ((u32)base[rp * CS + spc0] + (u32)base[rq * CS + spc0] + 2u)) >> 2;
+                        } else {
+                            const u32 y0 = base[2 * j * CS + 8], y1 = (j == 1) ? y0 : (j == 7 ? 0u : (u32)base[(2 * j + 2) * CS + 8]);
+                            pv = (3u * (y0 + y1 + 2u)) >> 2;
+                        }
+                    }
+                    const u32 keep = sel0 ? 0xffff0000u : 0x0000ffffu, ins = sel0 ? pv : pv << 16;
+                    Nh = (Nh & keep) | ins;
+                    Fh = (Fh & keep) | ins;
+                    hfilter16(Nh, N, E0[c], O0[c]);
+                    hfilter16(Fh, F, E1[c], O1[c]);
+                    if (firstvec && cc0 == 0) E1[c][0] = prmt(E1[c][0], O1[c][0], 0x3254u);   // far rows: out[0] = out[1] (avx2.rs:330)
+                } else {
+                    // last 32 outputs of the double-row: out[O+2k] = T(in[c], in[c-1]), out[O+2k+1] = T(in[c], in[c+1]),
+                    // c = (row end) - 33 + k: raw row 2j+1 (near) / 2j+3 (far), no vertical blend; k = 15 repeats k = 14
+                    // (upsampler/avx2.rs:277-307,332-338; Q4g)
+                    const int q = (cc0 - (W - 16)) >> 3;                      // which half of the 32 outputs
+                    const int lq = 8 + (W - 36 + 8 * q - cb0 * 8);            // smem column of c - 3 for k = 8q (multiple of 4)
+#pragma unroll
+                    for (int f = 0; f < 2; f++) {
+                        const u32 *pw = reinterpret_cast<const u32 *>(base + (f ? rb : ra) * CS + lq);
+                        const u32 w0 = pw[0], w1 = pw[1], w2 = pw[2];
+                        const u32 r[4] = {prmt(w0, w1, 0x0403u) & 0x00ff00ffu, prmt(w1, 0u, 0x4241u), prmt(w1, w2, 0x0403u) & 0x00ff00ffu, prmt(w2, 0u, 0x4241u)};
+                        const u32 h = prmt(w0, w2, 0x0702u) & 0x00ff00ffu;
+                        u32 *E = f ? E1[c] : E0[c], *O = f ? O1[c] : O0[c];
+                        hfilter16(h, r, E, O);
+                        if (q == 1) { E[3] = prmt(E[3], 0u, 0x1010u); O[3] = prmt(O[3], 0u, 0x1010u); }
+                    }
+                }
+            }
+            if (y_base + yl0 < im.height) {
+                u32 yw[4];
+                if (FT::H == 2) { const uint4 v = *reinterpret_cast<const uint4 *>(yrow0); yw[0] = v.x; yw[1] = v.y; yw[2] = v.z; yw[3] = v.w; }
+                else { const uint2 v0 = *reinterpret_cast<const uint2 *>(yrow0), v1 = *reinterpret_cast<const uint2 *>(yrow0 + 8); yw[0] = v0.x; yw[1] = v0.y; yw[2] = v1.x; yw[3] = v1.y; }
+                emit16(out + (size_t)(y_base + yl0) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec);
+            }
+            if (RPU == 2 && y_base + yl1 < im.height) {
+                u32 yw[4];
+                if (FT::H == 2) { const uint4 v = *reinterpret_cast<const uint4 *>(yrow1); yw[0] = v.x; yw[1] = v.y; yw[2] = v.z; yw[3] = v.w; }
+                else { const uint2 v0 = *reinterpret_cast<const uint2 *>(yrow1), v1 = *reinterpret_cast<const uint2 *>(yrow1 + 8); yw[0] = v0.x; yw[1] = v0.y; yw[2] = v1.x; yw[3] = v1.y; }
+                emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec);
+            }
+        }
+        if (nslow > 0) {
+            SlowCtx<ST> sc;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                sc.cv[c].base = sC[c]; sc.cv[c].W = W; sc.cv[c].n = FT::CROWS * W;
+                sc.cv[c].c0 = cb0 * 8; sc.cv[c].c1 = (cb0 + ncb) * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS; sc.cv[c].magic_w = im.magic_w;
+            }
+            sc.sY = sY; sc.twy = TWY; sc.X0 = X0; sc.Wp = Wp; sc.hv_avx = (int)im.hv_avx; sc.y_base = y_base; sc.height = im.height;
+            sc.stride = stride; sc.n_norm = n_norm; sc.T = T; sc.ycc = ycc; sc.out = out; sc.width = im.width; sc.nc = im.nc;
+            if (nslow > ZJ_SLOW_CAP) {
+                const int tw = nyb * 8;
+                for (int u = tid; u < ROWS * tw; u += ZF_THREADS) { const int yl = u / tw; slow_pixel<MODE, 0, ST>(sc, yl, u - yl * tw); }
+            } else {
+                for (int t = tid; t < nslow * 16 * RPU; t += ZF_THREADS) {
+                    const int e = sSlow[t / (16 * RPU)], r = (t >> 4) % RPU, k = t & 15;
+                    const int g = e >> 8, xl2 = (e & 0xff) << 3;
+                    int yl;
+                    if (MODE == MODE_V) yl = 2 * g + r;
+                    else if (MODE == MODE_HV) yl = 4 * (g >> 1) + (g & 1) + 2 * r;
+                    else yl = g;
+                    if (xl2 + k < nyb * 8) slow_pixel<MODE, 0, ST>(sc, yl, xl2 + k);
+                }
+            }
+        }
+        if (zcnt > 0) {
+            for (int u = tid; u < ROWS * zcnt; u += ZF_THREADS) {
+                const int yl = u / zcnt, k = u - yl * zcnt;
+                const u32 y = y_base + yl;
+                if (y >= im.height) break;
+                uint8_t *z = out + (size_t)y * stride + zb0 + (size_t)k * zg;
+                if (zg == 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0u, 0u, 0u, 0u);
+                else if (zg == 4) *reinterpret_cast<u32 *>(z) = 0u;
+                else *z = 0;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------- luma-only kernel
 // (YCbCr | GRAYSCALE) -> GRAYSCALE: IDCT of the Y plane only (worker.rs:59,115-118), `as u8` row copy
 // (color_convert/scalar.rs:91-114; Q7 is resolved on the host: geometries where the reference panics are
@@ -921,8 +1311,31 @@ static cudaError_t launch_reconstruct(const DevImage *d_images, const LaunchGrou
     return cudaGetLastError();
 }
 
+static int g_spc = 0;  // strips per CTA of the fast kernel (0 = default; ZJ_SPC in the environment overrides)
+
+template <int MODE>
+static cudaError_t launch_fast(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
+{
+    if (g_spc == 0) {
+        const char *e = getenv("ZJ_SPC");
+        g_spc = e ? atoi(e) : ZF_DEFAULT_SPC;
+        if (g_spc < 1) g_spc = 1;
+    }
+    dim3 grid(g.max_tiles, (g.max_strips + g_spc - 1) / g_spc + 1, g.count);
+    reconstruct_fast_kernel<MODE><<<grid, ZF_THREADS, 0, stream>>>(d_images + g.first, g_spc);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_group(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
 {
+    if (g.fast) {
+        switch (g.mode) {
+        case MODE_NONE: return launch_fast<MODE_NONE>(d_images, g, stream);
+        case MODE_H: return launch_fast<MODE_H>(d_images, g, stream);
+        case MODE_V: return launch_fast<MODE_V>(d_images, g, stream);
+        default: return launch_fast<MODE_HV>(d_images, g, stream);
+        }
+    }
     if (g.gray) {
         const int rows = g.mode == MODE_NONE ? 8 : (g.mode == MODE_HV ? 32 : 16);
         dim3 grid(g.max_tiles, g.max_strips * (rows >> 3) + 1, g.count);
