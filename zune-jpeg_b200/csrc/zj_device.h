@@ -32,18 +32,19 @@ constexpr int ZJ_SLOW_CAP = 192;  // edge units per tile queued for the generic 
 // tile widths scale with the CTA size (128 threads: 40 / 15 / 32 / 10)
 constexpr int TM_NONE = 40 * ZJ_THREADS / 128, TM_H = 15 * ZJ_THREADS / 128, TM_V = 32 * ZJ_THREADS / 128, TM_HV = 10 * ZJ_THREADS / 128, TM_GRAY = 128;
 
-// The fast kernel (X86 variant): 256 threads, every thread owns one 8x8 block and one 16-sample unit per strip.
+// The fast kernel (X86 variant): 256 threads = 128 producers (IDCT, two 8x8 blocks per thread and strip) + 128
+// consumers (up-sampling / colour / stores, two 16-sample units per thread and strip).
 #ifndef ZF_CFG_MINBLOCKS
 #define ZF_CFG_MINBLOCKS 3
 #endif
 #ifndef ZF_CFG_SPC
-#define ZF_CFG_SPC 4
+#define ZF_CFG_SPC 16
 #endif
-constexpr int ZF_THREADS = 256;
+constexpr int ZF_THREADS = 256, ZF_PRODUCERS = 128, ZF_CONSUMERS = 128;
 constexpr int ZF_MINBLOCKS = ZF_CFG_MINBLOCKS;
 constexpr int ZF_DEFAULT_SPC = ZF_CFG_SPC;      // strips per CTA
-// unit columns (16 luma samples) per tile: ZF_THREADS / row groups per strip
-constexpr int ZF_XU_NONE = ZF_THREADS / 8, ZF_XU_H = ZF_THREADS / 16, ZF_XU_V = ZF_THREADS / 8, ZF_XU_HV = ZF_THREADS / 16;
+// unit columns (16 luma samples) per tile: 2 * ZF_CONSUMERS / row groups per strip
+constexpr int ZF_XU_NONE = 2 * ZF_CONSUMERS / 8, ZF_XU_H = 2 * ZF_CONSUMERS / 16, ZF_XU_V = 2 * ZF_CONSUMERS / 8, ZF_XU_HV = 2 * ZF_CONSUMERS / 16;
 
 struct DevImage {
     const int16_t *coeff[3];  // device pointers, whole-image planes

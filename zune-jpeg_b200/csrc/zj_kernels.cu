@@ -867,11 +867,16 @@ reconstruct_kernel(const DevImage *__restrict__ images)
 }
 
 // =========================================================================== the fast kernel (X86 variant)
-// Same arithmetic as above, organised so that nothing is decided twice: a CTA of 256 threads owns one tile column
-// of `spc` consecutive strips; in every strip each thread transforms (at most) ONE 8x8 block and then produces ONE
-// unit = 16 luma columns (one conv16 chunk of the reference, color_convert/avx.rs:67-107) of one output row
-// (NONE, H) or of the two rows that share their chroma inputs (V, HV).  Everything that depends only on the
-// thread's position in the tile -- block pointers, the row writer's placement rule, the AVX2 lane of the unit,
+// Same arithmetic as above, organised as a producer / consumer pipeline inside one CTA of 256 threads that owns one
+// tile column of `spc` consecutive strips:
+//   * warps 0-3 (producers) run the IDCT: two passes of one 8x8 block per thread fill the strip's sample planes in
+//     shared memory (double-buffered), the next strip's coefficients are prefetched into L2 on the way;
+//   * warps 4-7 (consumers) turn the planes into pixels: every thread produces two UNITS per strip, a unit being 16
+//     luma columns (one conv16 chunk of the reference, color_convert/avx.rs:67-107) of one output row (NONE, H) or
+//     of the two rows that share their chroma inputs (V, HV).
+// The two halves meet only at named barriers (full / empty per buffer), so the integer-multiply-heavy IDCT of strip
+// s+1 overlaps the byte-shuffling colour stage of strip s on every SM sub-partition.  Everything that depends only
+// on the thread's position in the tile -- block pointers, the row writer's placement rule, the AVX2 lane of the unit,
 // neighbour offsets -- is computed once, before the strip loop.  Units the packed code does not cover are queued
 // once and handled per sample by the generic path (slow_pixel) in every strip.
 template <int MODE> struct FastTraits {
@@ -881,18 +886,25 @@ template <int MODE> struct FastTraits {
     static constexpr int CROWS = 8 * CBR;
     static constexpr int RPU = V;                     // rows per unit
     static constexpr int NRG = ROWS / RPU;            // row groups per strip
-    static constexpr int XU = ZF_THREADS / NRG;       // unit columns per tile
+    static constexpr int XU = 2 * ZF_CONSUMERS / NRG; // unit columns per tile (two units per consumer thread)
     static constexpr int TWY = 16 * XU;               // luma samples per tile row
     static constexpr int TWC = TWY / H;               // chroma samples per tile row
     static constexpr int YB = TWY / 8, CB = TWC / 8;  // blocks per block row of the tile
     static constexpr int CS = TWC + 24;               // chroma smem row: left halo | tile | right halo | special
     static constexpr int NSLOT = MODE == MODE_H ? 2 : (MODE == MODE_HV ? 3 : 0);  // halo block columns per chroma plane
     static constexpr int NY = YBR * YB, NC = CBR * CB, PER = NC + NSLOT * CBR;
-    static_assert(NY + 2 * PER <= ZF_THREADS, "one 8x8 block per thread");
+    static constexpr int YBYTES = ROWS * TWY, CBYTES = CROWS * CS, BUF = YBYTES + 2 * CBYTES;  // one buffer of sample planes
+    static_assert(NY + 2 * PER <= 2 * ZF_PRODUCERS, "two 8x8 blocks per producer thread");
+    static_assert(BUF % 16 == 0 && YBYTES % 16 == 0 && CBYTES % 8 == 0, "plane alignment");
 };
 
 __device__ __forceinline__ u32 evens(u32 w) { return prmt(w, 0u, 0x4240u); }  // bytes 0,2 -> 16-bit lanes
 __device__ __forceinline__ u32 odds(u32 w) { return prmt(w, 0u, 0x4341u); }   // bytes 1,3 -> 16-bit lanes
+
+// named barriers (id 0 is __syncthreads); count = every thread of the CTA: one half arrives, the other half waits
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ZF_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_sync_consumers(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ZF_CONSUMERS) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ZF_THREADS) : "memory"); }
 
 // Horizontal x2 triangle filter of eight samples R0..R7 (r[k] = (R2k, R2k+1) as lane pairs) with outer neighbours
 // h = (R(-1), R8):  out[2i] = T(R[i], R[i-1]), out[2i+1] = T(R[i], R[i+1])  (upsampler/scalar.rs:30-42 == avx2.rs:178-197)
@@ -951,6 +963,17 @@ __device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 
     }
 }
 
+__device__ __forceinline__ void load16(const uint8_t *p, const bool a16, u32 w[4])
+{
+    if (a16) { const uint4 v = *reinterpret_cast<const uint4 *>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    else { const uint2 v0 = *reinterpret_cast<const uint2 *>(p), v1 = *reinterpret_cast<const uint2 *>(p + 8); w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y; }
+}
+
+#ifndef ZF_PREFETCH
+#define ZF_PREFETCH 1   // next strip's coefficients: 0 nothing, 1 prefetch.global.L2, 2 prefetch.global.L1
+#endif
+enum { BAR_FULL = 1, BAR_EMPTY = 3 };  // + buffer index
+
 template <int MODE>
 __global__ void __launch_bounds__(ZF_THREADS, ZF_MINBLOCKS)
 reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
@@ -960,11 +983,10 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     constexpr int ROWS = FT::ROWS, TWY = FT::TWY, CS = FT::CS, NRG = FT::NRG, XU = FT::XU, RPU = FT::RPU;
     constexpr bool HALO = FT::NSLOT > 0;
 
-    __shared__ __align__(16) ST sY[ROWS * TWY];
-    __shared__ __align__(16) ST sC[2][FT::CROWS * CS];
+    __shared__ __align__(16) ST sPlanes[2][FT::BUF];   // [buffer][Y | Cb | Cr]
     __shared__ u32 sQ[3][32];
     __shared__ int sSlowN;
-    __shared__ unsigned short sSlow[ZJ_SLOW_CAP];  // units left to the generic path (row group << 8 | tile column / 8)
+    __shared__ unsigned short sSlow[ZJ_SLOW_CAP];      // units left to the generic path (row group << 8 | tile column / 8)
 
     const DevImage &im = images[blockIdx.z];
     const u32 tile = blockIdx.x;
@@ -987,7 +1009,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         for (size_t b = b0 + tid; b < b1; b += ZF_THREADS) out[b] = 0;
         return;
     }
-    const u32 s_end = min(s_begin + (u32)spc, n_strips);
+    const int n_it = (int)(min(s_begin + (u32)spc, n_strips) - s_begin);   // strips of this CTA
 
     // tile -> unit columns [u0, u1) (16 luma samples each), spread evenly: the first tile_r tiles are one wider
     const int nt = (int)im.n_tiles;
@@ -996,55 +1018,90 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const int X0 = 16 * u0;                                        // first luma column of the tile
     const int yb0 = 2 * u0, nyb = min(2 * u1, Wp >> 3) - yb0;      // luma block columns of the tile
     const int cb0 = FT::H == 2 ? u0 : yb0, ncb = FT::H == 2 ? u1 - u0 : nyb;  // chroma block columns
-    const bool last_tile = (tile + 1 == (u32)nt);
     // halo block columns wrap around the image: the flat filters run across row ends (Q4a); tile 0 of the AVX2 HV
     // form also needs block column mcu_x-2 for the stale first-vector neighbours (Q4f)
     const int lhb = HALO ? (cb0 == 0 ? mcu_x - 1 : cb0 - 1) : -1;
     const int rhb = HALO ? (cb0 + ncb == mcu_x ? 0 : cb0 + ncb) : -1;
     const int spb = (MODE == MODE_HV && tile == 0 && nt > 1) ? mcu_x - 2 : -1;
-
-    // ------------------------------------------------------------ per-thread block of phase 1 (strip-invariant)
-    bool active;
-    const int16_t *src;
-    size_t src_step;          // i16 per strip
-    const u32 *qt;
-    ST *dst;
-    int dstride;
-    if (tid < FT::NY) {
-        const int br = tid / FT::YB, bc = tid % FT::YB;
-        active = bc < nyb;
-        const int ybpr = Wp >> 3;
-        src_step = (size_t)FT::YBR * ybpr * 64;
-        src = im.coeff[0] + (((size_t)s_begin * FT::YBR + br) * ybpr + yb0 + bc) * 64;
-        qt = sQ[0]; dst = sY + br * 8 * TWY + bc * 8; dstride = TWY;
-    } else {
-        int c = tid - FT::NY;
-        const int comp = c >= FT::PER ? 1 : 0;
-        c -= comp * FT::PER;
-        int br, gcol, lcol;
-        if (c < FT::NC) { br = c / FT::CB; const int bc = c % FT::CB; gcol = bc < ncb ? cb0 + bc : -1; lcol = 8 + bc * 8; }
-        else {
-            const int hi = c - FT::NC, slot = hi / FT::CBR;
-            br = hi % FT::CBR;
-            gcol = slot == 0 ? lhb : (slot == 1 ? rhb : spb);
-            lcol = slot == 0 ? 0 : (slot == 1 ? 8 + ncb * 8 : 16 + ncb * 8);
-            if (slot >= FT::NSLOT) gcol = -1;
-        }
-        active = comp < 2 && c < FT::PER && gcol >= 0;
-        src_step = (size_t)FT::CBR * mcu_x * 64;
-        src = im.coeff[1 + comp] + (((size_t)s_begin * FT::CBR + br) * mcu_x + (active ? gcol : 0)) * 64;
-        qt = sQ[1 + comp]; dst = sC[comp] + br * 8 * CS + lcol; dstride = CS;
-    }
-    if (!active) src = im.coeff[0];
-
-    // ------------------------------------------------------------ per-thread unit of phase 2 (strip-invariant)
-    const int xu = tid % XU, rg = tid / XU;
     const u32 n_norm = im.n_norm, T = im.T, P = im.P;
+
+    for (int k = tid; k < 96; k += ZF_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
+    if (tid == 0) sSlowN = 0;
+    __syncthreads();
+
+    if (tid < ZF_PRODUCERS) {
+        // ================================================================= producers: dequantise + IDCT
+        // blocks tid and tid + ZF_PRODUCERS of the tile's list [Y | Cb + halo | Cr + halo]; warps stay class-uniform
+        const int16_t *src[2];
+        u32 step[2], dsto[2], meta[2];   // i16 per strip; byte offset in the buffer; bit 0 active, bit 1 chroma, bits 2.. table
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++) {
+            const int b = tid + ps * ZF_PRODUCERS;
+            bool active;
+            if (b < FT::NY) {
+                const int br = b / FT::YB, bc = b % FT::YB;
+                active = bc < nyb;
+                const int ybpr = Wp >> 3;
+                step[ps] = (u32)(FT::YBR * ybpr * 64);
+                src[ps] = im.coeff[0] + (((size_t)s_begin * FT::YBR + br) * ybpr + yb0 + (active ? bc : 0)) * 64;
+                dsto[ps] = (u32)(br * 8 * TWY + bc * 8);
+                meta[ps] = (active ? 1u : 0u);
+            } else {
+                int c = b - FT::NY;
+                const int comp = c >= FT::PER ? 1 : 0;
+                c -= comp * FT::PER;
+                int br, gcol, lcol;
+                if (c < FT::NC) { br = c / FT::CB; const int bc = c % FT::CB; gcol = bc < ncb ? cb0 + bc : -1; lcol = 8 + bc * 8; }
+                else {
+                    const int hi = c - FT::NC, slot = hi / FT::CBR;
+                    br = hi % FT::CBR;
+                    gcol = slot == 0 ? lhb : (slot == 1 ? rhb : spb);
+                    lcol = slot == 0 ? 0 : (slot == 1 ? 8 + ncb * 8 : 16 + ncb * 8);
+                    if (slot >= FT::NSLOT) gcol = -1;
+                }
+                active = c < FT::PER && gcol >= 0;
+                step[ps] = (u32)(FT::CBR * mcu_x * 64);
+                src[ps] = im.coeff[1 + comp] + (((size_t)s_begin * FT::CBR + br) * mcu_x + (active ? gcol : 0)) * 64;
+                dsto[ps] = (u32)(FT::YBYTES + comp * FT::CBYTES + br * 8 * CS + lcol);
+                meta[ps] = (active ? 1u : 0u) | 2u | ((u32)(1 + comp) << 2);
+            }
+            if (!active) src[ps] = im.coeff[0];
+        }
+        // loop-carried state kept small (the IDCT needs nearly every register): two pointers, two packed words
+        const int16_t *src0 = src[0], *src1 = src[1];
+        const u32 pk0 = dsto[0] | (meta[0] << 16), pk1 = dsto[1] | (meta[1] << 16);
+        const u32 step0 = step[0], step1 = step[1];
+        for (int it = 0; it < n_it; it++) {
+            ST *planes = sPlanes[it & 1];
+#pragma unroll 1
+            for (int ps = 0; ps < 2; ps++) {
+                const u32 pk = ps ? pk1 : pk0;
+                const int16_t *sp = ps ? src1 : src0;
+                const bool active = (pk & 0x10000u) != 0;
+                int4 raw[8];
+                load_block(active, sp, raw);
+#if ZF_PREFETCH == 1
+                if (active && it + 1 < n_it) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (ps ? step1 : step0)));
+#elif ZF_PREFETCH == 2
+                if (active && it + 1 < n_it) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + (ps ? step1 : step0)));
+#endif
+                if (ps == 0 && it >= 2) bar_sync(BAR_EMPTY + (it & 1));   // the consumers are done with this buffer
+                idct_block<0, ST>(active, raw, sQ[pk >> 18], planes + (pk & 0xffffu), (pk & 0x20000u) ? CS : TWY);
+            }
+            src0 += step0; src1 += step1;
+            bar_arrive(BAR_FULL + (it & 1));
+        }
+        return;
+    }
+
+    // ===================================================================== consumers: up-sample, convert, write
+    const int tc = tid - ZF_PRODUCERS;
+    const int xu = tc % XU, rgA = tc / XU;                // this thread's units: (xu, rgA) and (xu, rgA + NRG/2)
     const bool ycc = im.out_kind == OUT_YCC;
-    int xs = X0 + 16 * xu;                          // first sample of the unit in the padded row
+    int xs = X0 + 16 * xu;                                // first sample of the unit in the padded row
     // Where the unit's 48 bytes go (worker.rs:201-246): samples < n_norm ("normal" 16-sample chunks) sit at
     // byte 3*s, except bytes the tail chunk overwrites; the tail chunk (samples Wp-16..Wp-1) sits at T; the rest is never written
-    int kind = 0;                                   // 0 = nothing to write, 1 = packed path, 2 = generic path
+    int kind = 0;                                         // 0 = nothing to write, 1 = packed path, 2 = generic path
     int dst_off = 3 * xs, nw = 12;
     if (u0 + xu < u1) {
         if ((u32)(xs + 16) <= n_norm) {
@@ -1064,47 +1121,38 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     }
     if (kind == 1 && (dst_off & 3) != 0) kind = 2;
     const bool vec = ((stride & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((dst_off & 15) == 0) && ((nw & 3) == 0);
-    const int xl = xs - X0;                          // tile-local luma column
-    // rows of the unit inside the strip
-    int yl0, yl1;
-    if (MODE == MODE_V) { yl0 = 2 * rg; yl1 = yl0 + 1; }
-    else if (MODE == MODE_HV) { yl0 = 4 * (rg >> 1) + (rg & 1); yl1 = yl0 + 2; }
-    else { yl0 = rg; yl1 = rg; }
-    // chroma geometry of the unit
-    const int cc0 = FT::H == 2 ? xs >> 1 : xs;       // first chroma column
-    const int lc = 8 + (cc0 - cb0 * 8);              // its smem column
+    const int xl = xs - X0;                               // tile-local luma column
+    const bool y16 = (xl & 15) == 0;
+    const int cc0 = FT::H == 2 ? xs >> 1 : xs;            // first chroma column
+    const int lc = 8 + (cc0 - cb0 * 8);                   // its smem column
     const bool first_x = HALO && cc0 == 0, last_x = HALO && cc0 + 8 == W;
-    int ra = 0, rb = 0, off0 = 0, off2 = 0;          // chroma rows blended (V, HV) and neighbour row offsets (flat filters)
+    // per-unit state of the two halves; the second unit sits ROWS/2 output rows (CROWS/2 chroma rows) below the first
+    int kindA = kind, kindB = kind;
+    int off0 = 0, off2 = 0;                               // row offsets of the outer neighbours (flat filters, Q4a)
     bool sel0 = false, firstvec = false, hv_tail = false;
-    if (MODE == MODE_V) {
-        ra = rg == 0 ? 0 : (rg == 7 ? 7 : rg); rb = rg == 0 ? 0 : (rg == 7 ? 7 : rg + 1);   // scalar.rs:64-147 (Q4c)
-    } else if (MODE == MODE_H) {
-        ra = rg;
+    const int pbit = rgA & 1;                             // HV: row parity inside the double-row
+    if (MODE == MODE_H) {
         off0 = first_x ? -CS : 0; off2 = last_x ? CS : 0;
         // strip start (out[0], out[1] edge rule) and strip end (scalar.rs:46-57 / the SSE tail Q4b) stay generic
-        if (kind == 1 && ((first_x && rg == 0) || (last_x && rg == NRG - 1))) kind = 2;
+        if (kind == 1 && first_x && rgA == 0) kindA = 2;
+        if (kind == 1 && last_x && rgA + NRG / 2 == NRG - 1) kindB = 2;
     } else if (MODE == MODE_HV) {
-        const int j = rg >> 1, p = rg & 1;
-        ra = 2 * j + p; rb = (j == 0 || j == 7) ? ra : ra + 2;       // double-row j blends chroma rows 2j+p and 2j+p+2 (Q4d)
-        off0 = (first_x && p) ? -CS : 0; off2 = last_x ? CS : 0;
-        sel0 = (((p ? W : 0) + cc0) & 15) == 0;                        // unit starts an AVX2 vector (else it ends one)
-        firstvec = p == 0 && cc0 < 16;                                 // vector t = 0 of the double-row (Q4f)
-        hv_tail = p == 1 && cc0 + 16 >= W;                             // last 32 outputs of the double-row (Q4g)
-        if (kind == 1 && hv_tail && W - 36 - cb0 * 8 < (cb0 == 0 ? 0 : -8)) kind = 2;  // raw tail reaches left of the tile's halo (or wraps a row)
-        if (kind == 1 && firstvec && W < 48) kind = 2;
+        off0 = (first_x && pbit) ? -CS : 0; off2 = last_x ? CS : 0;
+        sel0 = (((pbit ? W : 0) + cc0) & 15) == 0;        // unit starts an AVX2 vector (else it ends one)
+        firstvec = pbit == 0 && cc0 < 16;                 // vector t = 0 of the double-row (Q4f)
+        hv_tail = pbit == 1 && cc0 + 16 >= W;             // last 32 outputs of the double-row (Q4g)
+        if (kind == 1 && hv_tail && W - 36 - cb0 * 8 < (cb0 == 0 ? 0 : -8)) kindA = kindB = 2;  // raw tail reaches left of the tile's halo (or wraps a row)
+        if (kind == 1 && firstvec && W < 48) kindA = kindB = 2;
     }
-
-    for (int k = tid; k < 96; k += ZF_THREADS) sQ[k >> 5][k & 31] = im.qtw[k >> 5][k & 31];
-    if (tid == 0) sSlowN = 0;
-    __syncthreads();
-    if (kind == 2) {
-        const int slot = atomicAdd(&sSlowN, 1);
-        if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)((rg << 8) | (xl >> 3));
-    }
-    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        if ((h ? kindB : kindA) == 2) {
+            const int slot = atomicAdd(&sSlowN, 1);
+            if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)(((rgA + h * (NRG / 2)) << 8) | (xl >> 3));
+        }
+    bar_sync_consumers(5);   // the queue is complete (consumer warps only)
     const int nslow = sSlowN;
 
-    const uint8_t *const yrow0 = sY + yl0 * TWY + xl, *const yrow1 = sY + yl1 * TWY + xl;
     // bytes of a row nobody writes: [P, stride) minus the tail chunk [T, T+48) (Q5: 16 zero bytes; Q6: the w "alpha"
     // bytes) = [z0, stride); every tile zeroes its share, with the widest stores the alignment allows
     const u32 z0 = (T != 0xffffffffu && T + 48 > P) ? T + 48 : P;
@@ -1114,31 +1162,31 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const u32 zb0 = min(z0 + tile * zper, stride), zb1 = min(zb0 + zper, stride);
     const int zcnt = (int)((zb1 - zb0) / zg);                     // stores per row for this tile
 
-    for (u32 strip = s_begin; strip < s_end; strip++) {
-        // ------------------------------------------------------------ phase 1: IDCT into the shared planes
-        int4 raw[8];
-        load_block(active, src, raw);
-        src += src_step;
-        if (strip != s_begin) __syncthreads();         // the previous strip's readers are done with the planes
-        idct_block<0, ST>(active, raw, qt, dst, dstride);
-        __syncthreads();
-
-        // ------------------------------------------------------------ phase 2: up-sample, convert, write
-        const u32 y_base = strip * ROWS;
-        if (kind == 1) {
+    for (int it = 0; it < n_it; it++) {
+        const ST *planes = sPlanes[it & 1];
+        const u32 y_base = (s_begin + it) * ROWS;
+        bar_sync(BAR_FULL + (it & 1));
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            if ((h ? kindB : kindA) != 1) continue;
+            const int rg = rgA + h * (NRG / 2);
+            int yl0, yl1, ra, rb;                                     // rows of the unit inside the strip; chroma rows blended
+            if (MODE == MODE_V) { yl0 = 2 * rg; yl1 = yl0 + 1; ra = rg; rb = (rg == 0 || rg == 7) ? rg : rg + 1; }   // scalar.rs:64-147 (Q4c)
+            else if (MODE == MODE_HV) { const int j = rg >> 1; yl0 = 4 * j + pbit; yl1 = yl0 + 2; ra = 2 * j + pbit; rb = (j == 0 || j == 7) ? ra : ra + 2; }  // (Q4d)
+            else { yl0 = rg; yl1 = rg; ra = rg; rb = rg; }
             u32 E0[2][4], O0[2][4], E1[2][4], O1[2][4];   // [cb|cr] chroma of row 0 / row 1 of the unit, E/O arrangement
 #pragma unroll
             for (int c = 0; c < 2; c++) {
-                const uint8_t *base = sC[c];
+                const uint8_t *base = planes + FT::YBYTES + c * FT::CBYTES;
                 if (MODE == MODE_NONE) {
-                    const uint2 v0 = *reinterpret_cast<const uint2 *>(base + yl0 * CS + lc), v1 = *reinterpret_cast<const uint2 *>(base + yl0 * CS + lc + 8);
-                    const u32 w[4] = {v0.x, v0.y, v1.x, v1.y};
+                    u32 w[4];
+                    load16(base + ra * CS + lc, false, w);
 #pragma unroll
                     for (int k = 0; k < 4; k++) { E0[c][k] = evens(w[k]); O0[c][k] = odds(w[k]); }
                 } else if (MODE == MODE_V) {
-                    const uint2 a0 = *reinterpret_cast<const uint2 *>(base + ra * CS + lc), a1 = *reinterpret_cast<const uint2 *>(base + ra * CS + lc + 8);
-                    const uint2 b0 = *reinterpret_cast<const uint2 *>(base + rb * CS + lc), b1 = *reinterpret_cast<const uint2 *>(base + rb * CS + lc + 8);
-                    const u32 a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
+                    u32 a[4], b[4];
+                    load16(base + ra * CS + lc, false, a);
+                    load16(base + rb * CS + lc, false, b);
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const u32 aE = evens(a[k]), aO = odds(a[k]), bE = evens(b[k]), bO = odds(b[k]);
@@ -1148,9 +1196,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 } else if (MODE == MODE_H) {
                     const uint8_t *pa = base + ra * CS + lc;
                     const uint2 a = *reinterpret_cast<const uint2 *>(pa);
-                    const u32 h = (u32)pa[off0 - 1] | ((u32)pa[off2 + 8] << 16);
+                    const u32 hh = (u32)pa[off0 - 1] | ((u32)pa[off2 + 8] << 16);
                     const u32 r[4] = {lanes01(a.x), lanes23(a.x), lanes01(a.y), lanes23(a.y)};
-                    hfilter16(h, r, E0[c], O0[c]);
+                    hfilter16(hh, r, E0[c], O0[c]);
                 } else if (!hv_tail) {
                     const uint8_t *pa = base + ra * CS + lc, *pb = base + rb * CS + lc;
                     const uint2 a = *reinterpret_cast<const uint2 *>(pa), b = *reinterpret_cast<const uint2 *>(pb);
@@ -1197,23 +1245,21 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                         const u32 *pw = reinterpret_cast<const u32 *>(base + (f ? rb : ra) * CS + lq);
                         const u32 w0 = pw[0], w1 = pw[1], w2 = pw[2];
                         const u32 r[4] = {prmt(w0, w1, 0x0403u) & 0x00ff00ffu, prmt(w1, 0u, 0x4241u), prmt(w1, w2, 0x0403u) & 0x00ff00ffu, prmt(w2, 0u, 0x4241u)};
-                        const u32 h = prmt(w0, w2, 0x0702u) & 0x00ff00ffu;
+                        const u32 hh = prmt(w0, w2, 0x0702u) & 0x00ff00ffu;
                         u32 *E = f ? E1[c] : E0[c], *O = f ? O1[c] : O0[c];
-                        hfilter16(h, r, E, O);
+                        hfilter16(hh, r, E, O);
                         if (q == 1) { E[3] = prmt(E[3], 0u, 0x1010u); O[3] = prmt(O[3], 0u, 0x1010u); }
                     }
                 }
             }
             if (y_base + yl0 < im.height) {
                 u32 yw[4];
-                if (FT::H == 2) { const uint4 v = *reinterpret_cast<const uint4 *>(yrow0); yw[0] = v.x; yw[1] = v.y; yw[2] = v.z; yw[3] = v.w; }
-                else { const uint2 v0 = *reinterpret_cast<const uint2 *>(yrow0), v1 = *reinterpret_cast<const uint2 *>(yrow0 + 8); yw[0] = v0.x; yw[1] = v0.y; yw[2] = v1.x; yw[3] = v1.y; }
+                load16(planes + yl0 * TWY + xl, FT::H == 2 || y16, yw);
                 emit16(out + (size_t)(y_base + yl0) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec);
             }
             if (RPU == 2 && y_base + yl1 < im.height) {
                 u32 yw[4];
-                if (FT::H == 2) { const uint4 v = *reinterpret_cast<const uint4 *>(yrow1); yw[0] = v.x; yw[1] = v.y; yw[2] = v.z; yw[3] = v.w; }
-                else { const uint2 v0 = *reinterpret_cast<const uint2 *>(yrow1), v1 = *reinterpret_cast<const uint2 *>(yrow1 + 8); yw[0] = v0.x; yw[1] = v0.y; yw[2] = v1.x; yw[3] = v1.y; }
+                load16(planes + yl1 * TWY + xl, FT::H == 2 || y16, yw);
                 emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec);
             }
         }
@@ -1221,16 +1267,16 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             SlowCtx<ST> sc;
 #pragma unroll
             for (int c = 0; c < 2; c++) {
-                sc.cv[c].base = sC[c]; sc.cv[c].W = W; sc.cv[c].n = FT::CROWS * W;
+                sc.cv[c].base = planes + FT::YBYTES + c * FT::CBYTES; sc.cv[c].W = W; sc.cv[c].n = FT::CROWS * W;
                 sc.cv[c].c0 = cb0 * 8; sc.cv[c].c1 = (cb0 + ncb) * 8; sc.cv[c].lhb = lhb; sc.cv[c].rhb = rhb; sc.cv[c].spb = spb; sc.cv[c].cs = CS; sc.cv[c].magic_w = im.magic_w;
             }
-            sc.sY = sY; sc.twy = TWY; sc.X0 = X0; sc.Wp = Wp; sc.hv_avx = (int)im.hv_avx; sc.y_base = y_base; sc.height = im.height;
+            sc.sY = planes; sc.twy = TWY; sc.X0 = X0; sc.Wp = Wp; sc.hv_avx = (int)im.hv_avx; sc.y_base = y_base; sc.height = im.height;
             sc.stride = stride; sc.n_norm = n_norm; sc.T = T; sc.ycc = ycc; sc.out = out; sc.width = im.width; sc.nc = im.nc;
             if (nslow > ZJ_SLOW_CAP) {
                 const int tw = nyb * 8;
-                for (int u = tid; u < ROWS * tw; u += ZF_THREADS) { const int yl = u / tw; slow_pixel<MODE, 0, ST>(sc, yl, u - yl * tw); }
+                for (int u = tc; u < ROWS * tw; u += ZF_CONSUMERS) { const int yl = u / tw; slow_pixel<MODE, 0, ST>(sc, yl, u - yl * tw); }
             } else {
-                for (int t = tid; t < nslow * 16 * RPU; t += ZF_THREADS) {
+                for (int t = tc; t < nslow * 16 * RPU; t += ZF_CONSUMERS) {
                     const int e = sSlow[t / (16 * RPU)], r = (t >> 4) % RPU, k = t & 15;
                     const int g = e >> 8, xl2 = (e & 0xff) << 3;
                     int yl;
@@ -1241,8 +1287,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 }
             }
         }
+        if (it + 2 < n_it) bar_arrive(BAR_EMPTY + (it & 1));      // the producers may refill this buffer
         if (zcnt > 0) {
-            for (int u = tid; u < ROWS * zcnt; u += ZF_THREADS) {
+            for (int u = tc; u < ROWS * zcnt; u += ZF_CONSUMERS) {
                 const int yl = u / zcnt, k = u - yl * zcnt;
                 const u32 y = y_base + yl;
                 if (y >= im.height) break;
