@@ -231,6 +231,109 @@ __device__ __forceinline__ void idct_block(const bool active, const int4 (&raw)[
     }
 }
 
+// The IDCT of the fast kernel's producers (X86 variant, u8 planes), written as two short loops instead of one long
+// unrolled body so that it stays resident in the instruction cache next to the consumers' code:
+//   row pass:    row r of the block is read from the thread's staging slot (16-byte chunk r at sl ^ (r << 4)),
+//                dequantised and transformed; the eight 32-bit results go to the thread's scratch column (chunk k at
+//                sc + k * 16 * ZF_PRODUCERS: chunks 2r and 2r+1).  Rows that are zero in every block of the warp are
+//                skipped (a zero row transforms to exact zeros), rows without anything in columns 4-7 use the 4-input form;
+//   column pass: two groups of four columns, each read back as one 128-bit word per row, transformed, clamped and
+//                stored as four bytes per row.
+// Identical results to idct_block<0>: same 1-D kernels, same order (rows, then columns), same DC-only shortcut.
+__device__ __forceinline__ void lds128(u32 addr, u32 &a, u32 &b, u32 &c, u32 &d) { asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr)); }
+__device__ __forceinline__ void sts128(u32 addr, u32 a, u32 b, u32 c, u32 d) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory"); }
+
+// one row of the row pass: dequantise (IDP.2A: s16 x u8) + 1-D transform, results to scratch chunks k, k+1
+__device__ __forceinline__ void row_pass(const bool any, const bool anyhi, const u32 w0, const u32 w1, const u32 w2, const u32 w3,
+                                         const uint4 q, const u32 out)
+{
+    constexpr u32 CH = 16u * ZF_PRODUCERS;   // bytes between scratch chunks
+    if (!any) {                              // zero in every block of the warp: a zero row transforms to exact zeros
+        sts128(out, 0u, 0u, 0u, 0u);
+        sts128(out + CH, 0u, 0u, 0u, 0u);
+        return;
+    }
+    u32 s0 = dp2a_lo(w0, q.x), s1 = dp2a_hi(w0, q.x), s2 = dp2a_lo(w1, q.y), s3 = dp2a_hi(w1, q.y), s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+    if (anyhi) {
+        s4 = dp2a_lo(w2, q.z); s5 = dp2a_hi(w2, q.z); s6 = dp2a_lo(w3, q.w); s7 = dp2a_hi(w3, q.w);
+        idct8<10>(s0, s1, s2, s3, s4, s5, s6, s7, 512u);
+    } else {
+        idct8_lo4<10>(s0, s1, s2, s3, s4, s5, s6, s7, 512u);   // nothing in columns 4-7
+    }
+    sts128(out, s0, s1, s2, s3);
+    sts128(out + CH, s4, s5, s6, s7);
+}
+
+// four columns of the column pass: NIN input rows (the rest are zero in every block of the warp)
+template <int NIN>
+__device__ __forceinline__ void col_pass(const bool active, const bool dconly, const u32 dcword, const u32 in, uint8_t *__restrict__ out, const int stride)
+{
+    constexpr u32 CH = 16u * ZF_PRODUCERS;
+    const u32 SCALE_BITS = 512u + 65536u + (128u << 17);
+    u32 a[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (r < NIN) lds128(in + (u32)(2 * r) * CH, a[r][0], a[r][1], a[r][2], a[r][3]);
+        else a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (NIN == 4) idct8_lo4<17>(a[0][c], a[1][c], a[2][c], a[3][c], a[4][c], a[5][c], a[6][c], a[7][c], SCALE_BITS);
+        else idct8<17>(a[0][c], a[1][c], a[2][c], a[3][c], a[4][c], a[5][c], a[6][c], a[7][c], SCALE_BITS);
+    }
+    if (!active) return;
+    if (dconly) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) *reinterpret_cast<u32 *>(out + r * stride) = dcword;
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            *reinterpret_cast<u32 *>(out + r * stride) = pack_sat2((int)a[r][1], (int)a[r][0], pack_sat2((int)a[r][3], (int)a[r][2], 0u));   // clamps
+    }
+}
+
+template <typename AfterRows>
+__device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, const u32 sc, const u32 *__restrict__ qtw, uint8_t *__restrict__ dst, const int dst_stride,
+                                            AfterRows after_rows)
+{
+    constexpr u32 CH = 16u * ZF_PRODUCERS;
+    u32 acc = 0, acc47 = 0, dcmask = 0xffff0000u, dc0 = 0;
+#pragma unroll 1
+    for (int rp = 0; rp < 4; rp++) {          // rows 2rp, 2rp+1
+        u32 a0, a1, a2, a3, b0, b1, b2, b3;
+        const u32 pa = sl ^ (u32)(rp << 5);
+        lds128(pa, a0, a1, a2, a3);
+        lds128(pa ^ 16u, b0, b1, b2, b3);
+        const uint4 qa = *reinterpret_cast<const uint4 *>(qtw + rp * 8), qb = *reinterpret_cast<const uint4 *>(qtw + rp * 8 + 4);
+        if (rp == 0) dc0 = a0;
+        const u32 hi = a2 | a3 | b2 | b3, all = a0 | a1 | b0 | b1 | hi;
+        acc |= (a0 & dcmask) | a1 | b0 | b1 | hi;
+        dcmask = 0xffffffffu;
+        if (rp >= 2) acc47 |= all;
+        // the pair is skipped when it is zero in every block of the warp, and uses the 4-input form when nothing sits in columns 4-7
+        const bool any = __any_sync(0xffffffffu, all != 0), anyhi = __any_sync(0xffffffffu, hi != 0);
+        const u32 o = sc + (u32)(rp * 4) * CH;
+        row_pass(any, anyhi, a0, a1, a2, a3, qa, o);
+        row_pass(any, anyhi, b0, b1, b2, b3, qb, o + 2 * CH);
+    }
+    const bool rows47 = __any_sync(0xffffffffu, acc47 != 0);
+    after_rows();                             // every lane of the warp is done with its staging slot
+    // all 63 AC coefficients zero: ((c0 as i16).wrapping_mul(q0 as i16) >> 3) + 128 in i16, clamped (avx2.rs:159-167) --
+    // not what the full transform gives (Q3), so it is a per-block decision
+    const bool dconly = acc == 0;
+    const int dc = (int)(int16_t)(dc0 & 0xffffu), q0 = (int)(int16_t)(qtw[0] & 0xffu);
+    int v = (int)(int16_t)(dc * q0);
+    v = (int)(int16_t)((v >> 3) + 128);
+    const u32 dcword = (u32)max(min(v, 255), 0) * 0x01010101u;
+    if (!rows47) {                            // rows 4-7 are zero in every block of the warp
+#pragma unroll 1
+        for (int g = 0; g < 2; g++) col_pass<4>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
+    } else {
+#pragma unroll 1
+        for (int g = 0; g < 2; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- tile geometry
 template <int MODE> struct ModeTraits;
 template <> struct ModeTraits<MODE_NONE> { static constexpr int H = 1, V = 1, YBR = 1, CBR = 1, TM = TM_NONE, HALO = 0; };
@@ -969,10 +1072,16 @@ __device__ __forceinline__ void load16(const uint8_t *p, const bool a16, u32 w[4
     else { const uint2 v0 = *reinterpret_cast<const uint2 *>(p), v1 = *reinterpret_cast<const uint2 *>(p + 8); w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y; }
 }
 
+#ifndef ZF_NBUF
+#define ZF_NBUF 2
+#endif
+#ifndef ZF_ROLEMAP
+#define ZF_ROLEMAP 0    // 0: warps 0-3 produce, 4-7 consume (both roles on every SM sub-partition); 1: sub-partitions 0,1 produce, 2,3 consume
+#endif
 #ifndef ZF_PREFETCH
 #define ZF_PREFETCH 1   // next strip's coefficients: 0 nothing, 1 prefetch.global.L2, 2 prefetch.global.L1
 #endif
-enum { BAR_FULL = 1, BAR_EMPTY = 3 };  // + buffer index
+enum { BAR_FULL = 1, BAR_EMPTY = 1 + ZF_NBUF, BAR_QUEUE = 1 + 2 * ZF_NBUF };  // + buffer index
 
 template <int MODE>
 __global__ void __launch_bounds__(ZF_THREADS, ZF_MINBLOCKS)
@@ -983,8 +1092,10 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     constexpr int ROWS = FT::ROWS, TWY = FT::TWY, CS = FT::CS, NRG = FT::NRG, XU = FT::XU, RPU = FT::RPU;
     constexpr bool HALO = FT::NSLOT > 0;
 
-    __shared__ __align__(16) ST sPlanes[2][FT::BUF];   // [buffer][Y | Cb | Cr]
-    __shared__ u32 sQ[3][32];
+    constexpr int NB = (MODE == MODE_V || MODE == MODE_NONE) ? 2 : ZF_NBUF;   // plane buffers in flight
+    extern __shared__ __align__(128) uint8_t sDynAll[];  // [staging slots ZF_PRODUCERS * 128 B | row-pass scratch ZF_PRODUCERS * 256 B | NB plane buffers of [Y | Cb | Cr]]
+    ST *const sPlanes = sDynAll + 3 * ZF_PRODUCERS * 128 + 128;   // (+ one all-zero slot)
+    __shared__ __align__(16) u32 sQ[3][32];
     __shared__ int sSlowN;
     __shared__ unsigned short sSlow[ZJ_SLOW_CAP];      // units left to the generic path (row group << 8 | tile column / 8)
 
@@ -1029,73 +1140,142 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     if (tid == 0) sSlowN = 0;
     __syncthreads();
 
-    if (tid < ZF_PRODUCERS) {
+#if ZF_ROLEMAP == 1
+    const int warp = tid >> 5;
+    const bool producer = (warp & 2) == 0;
+    const int rtid = ((warp >> 2) * 64) + ((warp & 1) * 32) + (tid & 31);   // thread index inside the role
+#else
+    const bool producer = tid < ZF_PRODUCERS;
+    const int rtid = producer ? tid : tid - ZF_PRODUCERS;
+#endif
+    if (producer) {
         // ================================================================= producers: dequantise + IDCT
-        // blocks tid and tid + ZF_PRODUCERS of the tile's list [Y | Cb + halo | Cr + halo]; warps stay class-uniform
-        const int16_t *src[2];
-        u32 step[2], dsto[2], meta[2];   // i16 per strip; byte offset in the buffer; bit 0 active, bit 1 chroma, bits 2.. table
+        // Blocks rtid and rtid + ZF_PRODUCERS of the tile's list [Y | Cb tile | Cr tile | Cb halo | Cr halo]: every warp
+        // owns 32 consecutive entries = one or two contiguous runs of blocks in global memory (or up to 32 lone halo
+        // blocks).  The warp copies its runs with fully coalesced cp.async into its 32 staging slots (128 bytes each,
+        // 16-byte chunks XOR-swizzled by the slot number so that the per-thread 128-bit reads are conflict-free),
+        // one strip ahead of the arithmetic.
+        constexpr int NHB = FT::NSLOT * FT::CBR;                  // halo blocks per chroma plane
+        const int lane = tid & 31, wq = rtid >> 5;
+        const int ybpr = Wp >> 3;
+        // block index -> plane, block row, global block column (-1: none), smem column
+        auto decode = [&](int b, int &comp, int &br, int &gcol, int &lcol) {
+            if (b < FT::NY) { comp = 0; br = b / FT::YB; const int bc = b % FT::YB; gcol = bc < nyb ? yb0 + bc : -1; lcol = bc * 8; }
+            else if (b < FT::NY + 2 * FT::NC) {
+                int c = b - FT::NY; comp = 1 + c / FT::NC; c %= FT::NC;
+                br = c / FT::CB; const int bc = c % FT::CB; gcol = bc < ncb ? cb0 + bc : -1; lcol = 8 + bc * 8;
+            } else {
+                int hx = b - FT::NY - 2 * FT::NC; comp = 1 + hx / (NHB > 0 ? NHB : 1); hx %= (NHB > 0 ? NHB : 1);
+                const int slot = hx / FT::CBR; br = hx % FT::CBR;
+                gcol = slot == 0 ? lhb : (slot == 1 ? rhb : spb);
+                lcol = slot == 0 ? 0 : (slot == 1 ? 8 + ncb * 8 : 16 + ncb * 8);
+                if (NHB == 0 || comp > 2) { comp = 1; gcol = -1; }
+            }
+        };
+        auto block_ptr = [&](int comp, int br, int gcol) -> const int16_t * {
+            return comp == 0 ? im.coeff[0] + (((size_t)s_begin * FT::YBR + br) * ybpr + gcol) * 64
+                             : im.coeff[comp] + (((size_t)s_begin * FT::CBR + br) * mcu_x + gcol) * 64;
+        };
+        const u32 stepY = (u32)(FT::YBR * ybpr * 64), stepC = (u32)(FT::CBR * mcu_x * 64);   // i16 per strip
+        // this thread's own two blocks: where the samples go, which table
+        u32 pk[2];                       // bits 0-15 byte offset in the plane buffer, 16 active, 17 chroma, 18-19 table
+        // this warp's staging jobs
+        const int16_t *q0[2], *q1[2];    // lane pointers into run 0 / run 1 (mode 3: the lane's own block)
+        u32 jm[2];                       // bits 0-7 lim0, 8-15 lim1 (+64 bias), 16-17 mode: 0 none, 1 one run of 32, 2 two runs of 16, 3 lone blocks
 #pragma unroll
         for (int ps = 0; ps < 2; ps++) {
-            const int b = tid + ps * ZF_PRODUCERS;
-            bool active;
-            if (b < FT::NY) {
-                const int br = b / FT::YB, bc = b % FT::YB;
-                active = bc < nyb;
-                const int ybpr = Wp >> 3;
-                step[ps] = (u32)(FT::YBR * ybpr * 64);
-                src[ps] = im.coeff[0] + (((size_t)s_begin * FT::YBR + br) * ybpr + yb0 + (active ? bc : 0)) * 64;
-                dsto[ps] = (u32)(br * 8 * TWY + bc * 8);
-                meta[ps] = (active ? 1u : 0u);
-            } else {
-                int c = b - FT::NY;
-                const int comp = c >= FT::PER ? 1 : 0;
-                c -= comp * FT::PER;
-                int br, gcol, lcol;
-                if (c < FT::NC) { br = c / FT::CB; const int bc = c % FT::CB; gcol = bc < ncb ? cb0 + bc : -1; lcol = 8 + bc * 8; }
+            int comp, br, gcol, lcol;
+            decode(rtid + ps * ZF_PRODUCERS, comp, br, gcol, lcol);
+            const bool active = gcol >= 0;
+            pk[ps] = (comp == 0 ? (u32)(br * 8 * TWY + lcol) : (u32)(FT::YBYTES + (comp - 1) * FT::CBYTES + br * 8 * CS + lcol)) |
+                     (active ? 0x10000u : 0u) | (comp ? 0x20000u : 0u) | ((u32)comp << 18);
+            const int B0 = ps * ZF_PRODUCERS + wq * 32;          // first block of the warp
+            const int lsub = lane >> 3, lch = lane & 7;
+            q0[ps] = q1[ps] = im.coeff[0];
+            int mode = 0, lim0 = 0, lim1 = 0;
+            if (B0 < FT::NY + 2 * FT::NC) {
+                int c0, b0r, g0, l0;
+                decode(B0, c0, b0r, g0, l0);
+                const bool isY = B0 < FT::NY;
+                const int bpr = isY ? FT::YB : FT::CB;           // blocks per tile block row
+                const int col0 = isY ? (B0 % FT::YB) : ((B0 - FT::NY) % FT::NC) % FT::CB;
+                const int have = (isY ? nyb : ncb) - col0;       // valid blocks from col0 on
+                const int first = (isY ? yb0 : cb0) + col0;
+                if (bpr >= 32) { mode = 1; lim0 = min(max(have, 0), 32) - lsub; q0[ps] = block_ptr(c0, b0r, first) + lsub * 64 + lch * 8; }
                 else {
-                    const int hi = c - FT::NC, slot = hi / FT::CBR;
-                    br = hi % FT::CBR;
-                    gcol = slot == 0 ? lhb : (slot == 1 ? rhb : spb);
-                    lcol = slot == 0 ? 0 : (slot == 1 ? 8 + ncb * 8 : 16 + ncb * 8);
-                    if (slot >= FT::NSLOT) gcol = -1;
+                    mode = 2; lim0 = lim1 = min(max(have, 0), 16) - lsub;
+                    q0[ps] = block_ptr(c0, b0r, first) + lsub * 64 + lch * 8;
+                    q1[ps] = block_ptr(c0, b0r + 1, first) + lsub * 64 + lch * 8;
                 }
-                active = c < FT::PER && gcol >= 0;
-                step[ps] = (u32)(FT::CBR * mcu_x * 64);
-                src[ps] = im.coeff[1 + comp] + (((size_t)s_begin * FT::CBR + br) * mcu_x + (active ? gcol : 0)) * 64;
-                dsto[ps] = (u32)(FT::YBYTES + comp * FT::CBYTES + br * 8 * CS + lcol);
-                meta[ps] = (active ? 1u : 0u) | 2u | ((u32)(1 + comp) << 2);
+            } else if (active) { mode = 3; q0[ps] = block_ptr(comp, br, gcol); }
+            // bit k: chunk k of the cooperative copy is inside the run; bit 8: the lane copies its own (lone) block
+            u32 m = 0;
+            for (int k = 0; k < 8; k++) {
+                const bool second = mode == 2 && k >= 4;
+                if ((mode == 1 || mode == 2) && 4 * (second ? k - 4 : k) < (second ? lim1 : lim0)) m |= 1u << k;
             }
-            if (!active) src[ps] = im.coeff[0];
+            if (mode == 3) m = 0x100u;
+            if (mode == 2) q1[ps] -= 4 * 256;       // chunk k of run 1 is at q1 + (k - 4) * 256
+            else q1[ps] = q0[ps];
+            jm[ps] = m;
         }
-        // loop-carried state kept small (the IDCT needs nearly every register): two pointers, two packed words
-        const int16_t *src0 = src[0], *src1 = src[1];
-        const u32 pk0 = dsto[0] | (meta[0] << 16), pk1 = dsto[1] | (meta[1] << 16);
-        const u32 step0 = step[0], step1 = step[1];
+        const u32 stage0 = (u32)__cvta_generic_to_shared(sDynAll) + (u32)(wq * 32) * 128u;     // the warp's slots of pass 0 (pass 1: + 16 KB)
+        const u32 d_even = stage0 + (u32)(lane >> 3) * 128u + (u32)(((lane & 7) ^ (lane >> 3)) * 16);
+        const u32 d_odd = stage0 + (u32)(lane >> 3) * 128u + (u32)(((lane & 7) ^ ((lane >> 3) + 4)) * 16);
+        const u32 slx = (stage0 + (u32)lane * 128u) | (u32)((lane & 7) * 16);              // own slot, chunk r at slx ^ (r << 4)
+        const u32 scr = (u32)__cvta_generic_to_shared(sDynAll) + ZF_PRODUCERS * 128u + (u32)rtid * 16u;   // scratch column of the row pass
+        // threads without a block in a pass read an all-zero slot instead (their own slot may hold the other pass's block)
+        const u32 zslot = ((u32)__cvta_generic_to_shared(sDynAll) + 3u * ZF_PRODUCERS * 128u) | (u32)((lane & 7) * 16);
+        if (rtid < 8) sts128(zslot - (u32)((lane & 7) * 16) + (u32)rtid * 16u, 0u, 0u, 0u, 0u);
+        asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_QUEUE + 1), "n"(ZF_PRODUCERS) : "memory");   // producers only
+        auto issue = [&](const int ps, const int16_t *g0, const int16_t *g1, const u32 m) {
+            const u32 off = 0u;
+            if (m & 0x100u) {
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((slx + off) ^ (u32)(r << 4)), "l"(g0 + r * 8) : "memory");
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (m & (1u << k))
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(((k & 1) ? d_odd : d_even) + off + k * 512u), "l"((k < 4 ? g0 : g1) + k * 256) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // loop-carried state
+        const int16_t *qa0 = q0[0], *qb0 = q1[0], *qa1 = q0[1], *qb1 = q1[1];
+        const u32 pk0 = pk[0], pk1 = pk[1], jm0 = jm[0], jm1 = jm[1];
+        const u32 st0 = (wq * 32 < FT::NY) ? stepY : stepC, st1 = (ZF_PRODUCERS + wq * 32 < FT::NY) ? stepY : stepC;   // by the plane of the warp's blocks
+        // one staging slot per thread: the copy of the next pass is issued as soon as the row pass has drained the slot
+        // and lands while the column pass runs
+        const bool work0 = __any_sync(0xffffffffu, (pk0 & 0x10000u) != 0), work1 = __any_sync(0xffffffffu, (pk1 & 0x10000u) != 0);   // any block in the warp
+        issue(0, qa0, qb0, jm0);
+        qa0 += st0; qb0 += st0;
+        int buf = 0;
         for (int it = 0; it < n_it; it++) {
-            ST *planes = sPlanes[it & 1];
+            ST *planes = sPlanes + buf * FT::BUF;
 #pragma unroll 1
             for (int ps = 0; ps < 2; ps++) {
-                const u32 pk = ps ? pk1 : pk0;
-                const int16_t *sp = ps ? src1 : src0;
-                const bool active = (pk & 0x10000u) != 0;
-                int4 raw[8];
-                load_block(active, sp, raw);
-#if ZF_PREFETCH == 1
-                if (active && it + 1 < n_it) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (ps ? step1 : step0)));
-#elif ZF_PREFETCH == 2
-                if (active && it + 1 < n_it) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + (ps ? step1 : step0)));
-#endif
-                if (ps == 0 && it >= 2) bar_sync(BAR_EMPTY + (it & 1));   // the consumers are done with this buffer
-                idct_block<0, ST>(active, raw, sQ[pk >> 18], planes + (pk & 0xffffu), (pk & 0x20000u) ? CS : TWY);
+                const u32 pkk = ps ? pk1 : pk0;
+                const bool active = (pkk & 0x10000u) != 0;
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (ps == 0 && it >= NB) bar_sync(BAR_EMPTY + buf);   // the consumers are done with this buffer
+                auto refill = [&]() {
+                    if (ps == 0) { issue(1, qa1, qb1, jm1); qa1 += st1; qb1 += st1; }
+                    else if (it + 1 < n_it) { issue(0, qa0, qb0, jm0); qa0 += st0; qb0 += st0; }
+                };
+                if (ps ? work1 : work0) idct_rolled(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
+                else refill();
             }
-            src0 += step0; src1 += step1;
-            bar_arrive(BAR_FULL + (it & 1));
+            bar_arrive(BAR_FULL + buf);
+            buf = buf + 1 == NB ? 0 : buf + 1;
         }
         return;
     }
 
     // ===================================================================== consumers: up-sample, convert, write
-    const int tc = tid - ZF_PRODUCERS;
+    const int tc = rtid;
     const int xu = tc % XU, rgA = tc / XU;                // this thread's units: (xu, rgA) and (xu, rgA + NRG/2)
     const bool ycc = im.out_kind == OUT_YCC;
     int xs = X0 + 16 * xu;                                // first sample of the unit in the padded row
@@ -1150,7 +1330,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             const int slot = atomicAdd(&sSlowN, 1);
             if (slot < ZJ_SLOW_CAP) sSlow[slot] = (unsigned short)(((rgA + h * (NRG / 2)) << 8) | (xl >> 3));
         }
-    bar_sync_consumers(5);   // the queue is complete (consumer warps only)
+    bar_sync_consumers(BAR_QUEUE);   // the queue is complete (consumer warps only)
     const int nslow = sSlowN;
 
     // bytes of a row nobody writes: [P, stride) minus the tail chunk [T, T+48) (Q5: 16 zero bytes; Q6: the w "alpha"
@@ -1162,10 +1342,11 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const u32 zb0 = min(z0 + tile * zper, stride), zb1 = min(zb0 + zper, stride);
     const int zcnt = (int)((zb1 - zb0) / zg);                     // stores per row for this tile
 
+    int buf = 0;
     for (int it = 0; it < n_it; it++) {
-        const ST *planes = sPlanes[it & 1];
+        const ST *planes = sPlanes + buf * FT::BUF;
         const u32 y_base = (s_begin + it) * ROWS;
-        bar_sync(BAR_FULL + (it & 1));
+        bar_sync(BAR_FULL + buf);
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             if ((h ? kindB : kindA) != 1) continue;
@@ -1287,7 +1468,8 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 }
             }
         }
-        if (it + 2 < n_it) bar_arrive(BAR_EMPTY + (it & 1));      // the producers may refill this buffer
+        if (it + NB < n_it) bar_arrive(BAR_EMPTY + buf);          // the producers may refill this buffer
+        buf = buf + 1 == NB ? 0 : buf + 1;
         if (zcnt > 0) {
             for (int u = tc; u < ROWS * zcnt; u += ZF_CONSUMERS) {
                 const int yl = u / zcnt, k = u - yl * zcnt;
@@ -1369,7 +1551,18 @@ static cudaError_t launch_fast(const DevImage *d_images, const LaunchGroup &g, c
         if (g_spc < 1) g_spc = 1;
     }
     dim3 grid(g.max_tiles, (g.max_strips + g_spc - 1) / g_spc + 1, g.count);
-    reconstruct_fast_kernel<MODE><<<grid, ZF_THREADS, 0, stream>>>(d_images + g.first, g_spc);
+    typedef FastTraits<MODE> FT;
+    constexpr int NB = (MODE == MODE_V || MODE == MODE_NONE) ? 2 : ZF_NBUF;
+    constexpr size_t smem = 3 * ZF_PRODUCERS * 128 + 128 + (size_t)NB * FT::BUF;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(reconstruct_fast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    reconstruct_fast_kernel<MODE><<<grid, ZF_THREADS, smem, stream>>>(d_images + g.first, g_spc);
     return cudaGetLastError();
 }
 
