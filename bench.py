@@ -345,7 +345,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(kernel_ms, 4),
-                "kernel": "zj::reconstruct_kernel (one launch per step covers the whole batch)"}
+                "kernel": ("zj::gray_kernel" if cfg == "c3_gray" else "zj::reconstruct_fast_kernel") + " (one launch per step covers the whole batch)"}
 
     if rank == 0:
         line = {

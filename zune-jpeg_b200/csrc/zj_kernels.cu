@@ -317,6 +317,7 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
         row_pass(any, anyhi, b0, b1, b2, b3, qb, o + 2 * CH);
     }
     const bool rows47 = __any_sync(0xffffffffu, acc47 != 0);
+    __syncwarp();
     after_rows();                             // every lane of the warp is done with its staging slot
     // all 63 AC coefficients zero: ((c0 as i16).wrapping_mul(q0 as i16) >> 3) + 128 in i16, clamped (avx2.rs:159-167) --
     // not what the full transform gives (Q3), so it is a per-block decision
