@@ -18,6 +18,17 @@
 
 #include "zj_device.h"
 
+// tuning switches of the fast kernel (tools/build_variant.sh)
+#ifndef ZF_T2PAIR
+#define ZF_T2PAIR 1
+#endif
+#ifndef ZF_LO6
+#define ZF_LO6 0
+#endif
+#ifndef ZF_EMIT_LOOP
+#define ZF_EMIT_LOOP 0
+#endif
+
 namespace zj {
 
 typedef uint32_t u32;
@@ -70,6 +81,33 @@ __device__ __forceinline__ void idct8_lo4(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u3
     const u32 p3 = c * (u32)(-8034);           // p3 = a + c = c
     const u32 p4 = d * (u32)(-1597);           // p4 = b + d = d
     const u32 dd = d * 6149u + q1 + p4, cc = c * 12586u + q2 + p3, bb = q2 + p4, aa = q1 + p3;
+    s0 = (u32)((int)(x0 + dd) >> SH);
+    s1 = (u32)((int)(x1 + cc) >> SH);
+    s2 = (u32)((int)(x2 + bb) >> SH);
+    s3 = (u32)((int)(x3 + aa) >> SH);
+    s4 = (u32)((int)(x3 - aa) >> SH);
+    s5 = (u32)((int)(x2 - bb) >> SH);
+    s6 = (u32)((int)(x1 - cc) >> SH);
+    s7 = (u32)((int)(x0 - dd) >> SH);
+}
+
+// The same 1-D kernel with s6 = s7 = 0 folded in: the column pass of blocks whose rows 6 and 7 are zero
+// (99 % of the luma blocks of a quality-90 photo).
+template <int SH>
+__device__ __forceinline__ void idct8_lo6(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s4, u32 &s5, u32 &s6, u32 &s7, const u32 bias)
+{
+    const u32 t2 = s2 * 2217u;                 // p1 + s6 * -7567 with s6 = 0
+    const u32 t3 = s2 * (2217u + 3135u);       // p1 + s2 * 3135
+    const u32 t0 = ((s0 + s4) << 12) + bias, t1 = ((s0 - s4) << 12) + bias;
+    const u32 x0 = t0 + t3, x3 = t0 - t3, x1 = t1 + t2, x2 = t1 - t2;
+    const u32 b = s5, c = s3, d = s1;          // a = s7 = 0
+    const u32 p4 = b + d, q2 = b + c;          // p3 = a + c = c, p1 = a + d = d
+    const u32 p5 = (c + p4) * 4816u;
+    const u32 r1 = p5 + d * (u32)(-3685);
+    const u32 r2 = p5 + q2 * (u32)(-10497);
+    const u32 m3 = c * (u32)(-8034);
+    const u32 m4 = p4 * (u32)(-1597);
+    const u32 dd = d * 6149u + r1 + m4, cc = c * 12586u + r2 + m3, bb = b * 8410u + r2 + m4, aa = r1 + m3;
     s0 = (u32)((int)(x0 + dd) >> SH);
     s1 = (u32)((int)(x1 + cc) >> SH);
     s2 = (u32)((int)(x2 + bb) >> SH);
@@ -279,6 +317,7 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         if (NIN == 4) idct8_lo4<17>(a[0][c], a[1][c], a[2][c], a[3][c], a[4][c], a[5][c], a[6][c], a[7][c], SCALE_BITS);
+        else if (NIN == 6) idct8_lo6<17>(a[0][c], a[1][c], a[2][c], a[3][c], a[4][c], a[5][c], a[6][c], a[7][c], SCALE_BITS);
         else idct8<17>(a[0][c], a[1][c], a[2][c], a[3][c], a[4][c], a[5][c], a[6][c], a[7][c], SCALE_BITS);
     }
     if (!active) return;
@@ -297,7 +336,7 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
                                             AfterRows after_rows)
 {
     constexpr u32 CH = 16u * ZF_PRODUCERS;
-    u32 acc = 0, acc47 = 0, dcmask = 0xffff0000u, dc0 = 0;
+    u32 acc = 0, acc47 = 0, acc67 = 0, dcmask = 0xffff0000u, dc0 = 0;
 #pragma unroll 1
     for (int rp = 0; rp < 4; rp++) {          // rows 2rp, 2rp+1
         u32 a0, a1, a2, a3, b0, b1, b2, b3;
@@ -310,13 +349,14 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
         acc |= (a0 & dcmask) | a1 | b0 | b1 | hi;
         dcmask = 0xffffffffu;
         if (rp >= 2) acc47 |= all;
+        if (rp == 3) acc67 = all;
         // the pair is skipped when it is zero in every block of the warp, and uses the 4-input form when nothing sits in columns 4-7
         const bool any = __any_sync(0xffffffffu, all != 0), anyhi = __any_sync(0xffffffffu, hi != 0);
         const u32 o = sc + (u32)(rp * 4) * CH;
         row_pass(any, anyhi, a0, a1, a2, a3, qa, o);
         row_pass(any, anyhi, b0, b1, b2, b3, qb, o + 2 * CH);
     }
-    const bool rows47 = __any_sync(0xffffffffu, acc47 != 0);
+    const bool rows47 = __any_sync(0xffffffffu, acc47 != 0), rows67 = __any_sync(0xffffffffu, acc67 != 0);
     __syncwarp();
     after_rows();                             // every lane of the warp is done with its staging slot
     // all 63 AC coefficients zero: ((c0 as i16).wrapping_mul(q0 as i16) >> 3) + 128 in i16, clamped (avx2.rs:159-167) --
@@ -329,6 +369,9 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
     if (!rows47) {                            // rows 4-7 are zero in every block of the warp
 #pragma unroll 1
         for (int g = 0; g < 2; g++) col_pass<4>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
+    } else if (ZF_LO6 && !rows67) {           // rows 6-7 are zero in every block of the warp
+#pragma unroll 1
+        for (int g = 0; g < 2; g++) col_pass<6>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
     } else {
 #pragma unroll 1
         for (int g = 0; g < 2; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
@@ -1002,6 +1045,18 @@ template <int MODE> struct FastTraits {
     static_assert(BUF % 16 == 0 && YBYTES % 16 == 0 && CBYTES % 8 == 0, "plane alignment");
 };
 
+// n = T(a, b), f = T(b, a) on both lanes, sharing a + b + 2:  3a + b + 2 = (a + b + 2) + 2a
+__device__ __forceinline__ void T2pair(u32 a, u32 b, u32 &n, u32 &f)
+{
+#if ZF_T2PAIR
+    const u32 s = a + b + 0x00020002u;
+    n = ((s + 2u * a) >> 2) & 0x00ff00ffu;
+    f = ((s + 2u * b) >> 2) & 0x00ff00ffu;
+#else
+    n = ((a * 3u + b + 0x00020002u) >> 2) & 0x00ff00ffu;
+    f = ((b * 3u + a + 0x00020002u) >> 2) & 0x00ff00ffu;
+#endif
+}
 __device__ __forceinline__ u32 evens(u32 w) { return prmt(w, 0u, 0x4240u); }  // bytes 0,2 -> 16-bit lanes
 __device__ __forceinline__ u32 odds(u32 w) { return prmt(w, 0u, 0x4341u); }   // bytes 1,3 -> 16-bit lanes
 
@@ -1372,8 +1427,8 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const u32 aE = evens(a[k]), aO = odds(a[k]), bE = evens(b[k]), bO = odds(b[k]);
-                        E0[c][k] = T2(aE, bE); O0[c][k] = T2(aO, bO);      // rows 2k, 2k+1 <- T(r_k, r_k+1), T(r_k+1, r_k)
-                        E1[c][k] = T2(bE, aE); O1[c][k] = T2(bO, aO);
+                        T2pair(aE, bE, E0[c][k], E1[c][k]);                // rows 2k, 2k+1 <- T(r_k, r_k+1), T(r_k+1, r_k)
+                        T2pair(aO, bO, O0[c][k], O1[c][k]);
                     }
                 } else if (MODE == MODE_H) {
                     const uint8_t *pa = base + ra * CS + lc;
@@ -1390,8 +1445,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     const u32 Ah = aL | (aR << 16), Bh = bL | (bR << 16);
                     u32 N[4], F[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { N[k] = T2(A[k], B[k]); F[k] = T2(B[k], A[k]); }
-                    u32 Nh = T2(Ah, Bh), Fh = T2(Bh, Ah);
+                    for (int k = 0; k < 4; k++) T2pair(A[k], B[k], N[k], F[k]);
+                    u32 Nh, Fh;
+                    T2pair(Ah, Bh, Nh, Fh);
                     // AVX2 form: lane 0 of a vector takes 3*(in+in'+2)>>2 of its OWN first element as "previous" value,
                     // lane 15 the same expression of the next vector's first element as "next" value (Q4e)
                     u32 pv = (3u * ((sel0 ? (a.x & 0xffu) + (b.x & 0xffu) : aR + bR) + 2u)) >> 2;
@@ -1434,6 +1490,25 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     }
                 }
             }
+#if ZF_EMIT_LOOP
+            // one copy of the colour / pack / store code (it is a third of the hot instructions): the second row's chroma
+            // is moved into the first row's registers between the two trips
+#pragma unroll 1
+            for (int row = 0; row < RPU; row++) {
+                const int yl = row ? yl1 : yl0;
+                if (y_base + yl < im.height) {
+                    u32 yw[4];
+                    load16(planes + yl * TWY + xl, FT::H == 2 || y16, yw);
+                    emit16(out + (size_t)(y_base + yl) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec);
+                }
+                if (RPU == 2) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { E0[c][k] = E1[c][k]; O0[c][k] = O1[c][k]; }
+                }
+            }
+#else
             if (y_base + yl0 < im.height) {
                 u32 yw[4];
                 load16(planes + yl0 * TWY + xl, FT::H == 2 || y16, yw);
@@ -1444,6 +1519,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 load16(planes + yl1 * TWY + xl, FT::H == 2 || y16, yw);
                 emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec);
             }
+#endif
         }
         if (nslow > 0) {
             SlowCtx<ST> sc;
