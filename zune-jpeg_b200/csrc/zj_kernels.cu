@@ -19,11 +19,27 @@
 #include "zj_device.h"
 
 // tuning switches of the fast kernel (tools/build_variant.sh)
+#ifndef ZF_HINTS
+#define ZF_HINTS 1
+#endif
 #ifndef ZF_T2PAIR
 #define ZF_T2PAIR 1
 #endif
 #ifndef ZF_LO6
 #define ZF_LO6 0
+#endif
+#if ZF_HINTS
+#define ZF_LIKELY(x) __builtin_expect(!!(x), 1)
+#define ZF_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define ZF_LIKELY(x) (x)
+#define ZF_UNLIKELY(x) (x)
+#endif
+#ifndef ZF_EXPERIMENT_SKIPC
+#define ZF_EXPERIMENT_SKIPC 0   // timing experiment only (wrong chroma): skip the pass-1 IDCT
+#endif
+#ifndef ZF_EXPERIMENT_PAD
+#define ZF_EXPERIMENT_PAD 0     // timing experiment only: extra dynamic shared memory per CTA (limits CTAs per SM)
 #endif
 #ifndef ZF_EMIT_LOOP
 #define ZF_EMIT_LOOP 0
@@ -321,7 +337,7 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
         else idct8<17>(a[0][c], a[1][c], a[2][c], a[3][c], a[4][c], a[5][c], a[6][c], a[7][c], SCALE_BITS);
     }
     if (!active) return;
-    if (dconly) {
+    if (ZF_UNLIKELY(dconly)) {
 #pragma unroll
         for (int r = 0; r < 8; r++) *reinterpret_cast<u32 *>(out + r * stride) = dcword;
     } else {
@@ -1109,7 +1125,7 @@ __device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 
         w[3 * k + 1] = prmt(gbO, rgE, 0x7610u);    // [G1 B1 R2 G2]
         w[3 * k + 2] = prmt(brO, gbO, 0x7632u);    // [B2 R3 G3 B3]
     }
-    if (vec && nw == 12) {
+    if (ZF_LIKELY(vec && nw == 12)) {
         uint4 *d = reinterpret_cast<uint4 *>(dst);
         d[0] = make_uint4(w[0], w[1], w[2], w[3]); d[1] = make_uint4(w[4], w[5], w[6], w[7]); d[2] = make_uint4(w[8], w[9], w[10], w[11]);
     } else if (vec && nw == 8) {
@@ -1321,7 +1337,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     if (ps == 0) { issue(1, qa1, qb1, jm1); qa1 += st1; qb1 += st1; }
                     else if (it + 1 < n_it) { issue(0, qa0, qb0, jm0); qa0 += st0; qb0 += st0; }
                 };
-                if (ps ? work1 : work0) idct_rolled(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
+                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
                 else refill();
             }
             bar_arrive(BAR_FULL + buf);
@@ -1436,7 +1452,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     const u32 hh = (u32)pa[off0 - 1] | ((u32)pa[off2 + 8] << 16);
                     const u32 r[4] = {lanes01(a.x), lanes23(a.x), lanes01(a.y), lanes23(a.y)};
                     hfilter16(hh, r, E0[c], O0[c]);
-                } else if (!hv_tail) {
+                } else if (ZF_LIKELY(!hv_tail)) {
                     const uint8_t *pa = base + ra * CS + lc, *pb = base + rb * CS + lc;
                     const uint2 a = *reinterpret_cast<const uint2 *>(pa), b = *reinterpret_cast<const uint2 *>(pb);
                     const u32 aL = pa[off0 - 1], aR = pa[off2 + 8], bL = pb[off0 - 1], bR = pb[off2 + 8];
@@ -1451,7 +1467,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     // AVX2 form: lane 0 of a vector takes 3*(in+in'+2)>>2 of its OWN first element as "previous" value,
                     // lane 15 the same expression of the next vector's first element as "next" value (Q4e)
                     u32 pv = (3u * ((sel0 ? (a.x & 0xffu) + (b.x & 0xffu) : aR + bR) + 2u)) >> 2;
-                    if (firstvec) {
+                    if (ZF_UNLIKELY(firstvec)) {
                         // vector t = 0: the neighbours are whatever the loop left behind (avx2.rs:67-68,264-270; Q4f): for
                         // j = 0 the raw in[0] / in[16], for j >= 1 the values computed 16 samples before the end of
                         // double-row j-1 (lane 0) and at the start of double-row j (lane 15), both with the stride of j-1
@@ -1521,7 +1537,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             }
 #endif
         }
-        if (nslow > 0) {
+        if (ZF_UNLIKELY(nslow > 0)) {
             SlowCtx<ST> sc;
 #pragma unroll
             for (int c = 0; c < 2; c++) {
@@ -1547,7 +1563,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         }
         if (it + NB < n_it) bar_arrive(BAR_EMPTY + buf);          // the producers may refill this buffer
         buf = buf + 1 == NB ? 0 : buf + 1;
-        if (zcnt > 0) {
+        if (ZF_UNLIKELY(zcnt > 0)) {
             for (int u = tc; u < ROWS * zcnt; u += ZF_CONSUMERS) {
                 const int yl = u / zcnt, k = u - yl * zcnt;
                 const u32 y = y_base + yl;
@@ -1630,7 +1646,7 @@ static cudaError_t launch_fast(const DevImage *d_images, const LaunchGroup &g, c
     dim3 grid(g.max_tiles, (g.max_strips + g_spc - 1) / g_spc + 1, g.count);
     typedef FastTraits<MODE> FT;
     constexpr int NB = (MODE == MODE_V || MODE == MODE_NONE) ? 2 : ZF_NBUF;
-    constexpr size_t smem = 3 * ZF_PRODUCERS * 128 + 128 + (size_t)NB * FT::BUF;
+    constexpr size_t smem = 3 * ZF_PRODUCERS * 128 + 128 + (size_t)NB * FT::BUF + ZF_EXPERIMENT_PAD;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
