@@ -119,7 +119,9 @@ ZJ_API int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, si
                               uint8_t *const *out, const size_t *out_len);
 
 /* DEVICE entry point: coefficient planes and outputs already live in the memory of `device`.
- * Asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream); no host<->device pixel traffic. */
+ * Asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream); no host<->device pixel traffic.
+ * Device coefficient planes must start on a 16-byte boundary (ZJ_ERR_INVALID_ARG otherwise; cudaMalloc'ed memory
+ * always does); outputs may have any alignment (4-byte aligned outputs take the fastest kernel). */
 ZJ_API int zj_gpu_reconstruct_device(int device, void *stream, const zj_image *imgs, size_t n,
                                      uint8_t *const *out_dev, const size_t *out_len);
 

@@ -117,3 +117,120 @@ def test_device_resident_batch_plan():
     got = out.download()
     assert np.array_equal(got, want)
     assert batch.algorithmic_bytes == sum(p.nbytes for p in planes) - 0 * 2 + len(want) or batch.algorithmic_bytes > 0
+
+
+# ------------------------------------------------------------------ the producer / consumer kernel's own corners
+def _device_case(rng, w, h, mode, out_cs, out_offset=0, coeff_offset=0):
+    """Device-resident planes / output at chosen byte offsets; returns (got, want) or the error status."""
+    from zune_jpeg_b200 import gpu
+    hs, vs = MODES[mode]
+    planes = util.random_planes(rng, w, h, 3, hs, vs)
+    host_img = util.make_image(w, h, planes, QTS, hs, vs, out_cs, 0)
+    want = oracle.reconstruct(host_img)
+    bufs = [gpu.DeviceBuffer(p.nbytes + 64) for p in planes]
+    for b, p in zip(bufs, planes):
+        b.upload(p, offset=coeff_offset)
+    out = gpu.DeviceBuffer(len(want) + 64)
+    out.memset(0xCD)
+    img = util.make_image(w, h, planes, QTS, hs, vs, out_cs, 0, ptrs=[b.ptr + coeff_offset for b in bufs])
+    try:
+        batch = gpu.Batch([img], [out.ptr + out_offset], [len(want)])
+    except gpu.ZjError as e:
+        return e.status, None
+    batch.run()
+    got = out.download()
+    assert np.all(got[:out_offset] == 0xCD) and np.all(got[out_offset + len(want):] == 0xCD), "wrote outside the output"
+    return got[out_offset:out_offset + len(want)], want
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_output_alignment_classes(mode):
+    """16-byte aligned rows take 128-bit stores, 4-byte aligned ones word stores, anything else the generic kernel."""
+    rng = np.random.default_rng(31)
+    for (w, h, out_cs) in [(640, 96, 0), (644, 64, 0), (1000, 70, 5), (333, 40, 0)]:
+        for off in (0, 4, 16, 1, 2):
+            got, want = _device_case(rng, w, h, mode, out_cs, out_offset=off)
+            assert np.array_equal(got, want), f"{w}x{h} {mode} out={out_cs} offset {off}"
+
+
+def test_misaligned_device_planes_are_refused():
+    rng = np.random.default_rng(32)
+    status, _ = _device_case(rng, 320, 64, "420", 0, coeff_offset=2)
+    assert status == -1  # ZJ_ERR_INVALID_ARG: device planes are read with 128-bit accesses
+
+
+def test_wide_and_partial_tiles():
+    """Many tiles per strip, a partial last tile, widths with W % 16 == 8, the "RGBA" zero columns spread over all tiles."""
+    rng = np.random.default_rng(33)
+    for (w, h, mode, out_cs) in [(8192, 64, "420", 5), (4100, 48, "420", 0), (4120, 40, "422", 0), (4104, 24, "444", 0),
+                                 (4104, 40, "440", 5), (2056, 70, "420", 2), (1032, 130, "420", 0), (264, 600, "420", 0)]:
+        assert _run_case(rng, w, h, mode, out_cs, 0) == "ok"
+
+
+@pytest.mark.parametrize("spc", [1, 2, 3, 5])
+def test_strips_per_cta(spc):
+    """ZJ_SPC (strips per CTA of the fast kernel) is read once per process: run the cases in a fresh interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "import oracle, util\n"
+        "from zune_jpeg_b200 import gpu\n"
+        "rng = np.random.default_rng(41)\n"
+        "qts = [util.std_qt(False), util.std_qt(True), util.std_qt(True)]\n"
+        "for (w, h, hs, vs, cs) in [(640, 480, 2, 2, 0), (320, 200, 1, 1, 0), (500, 330, 2, 1, 5), (256, 256, 1, 2, 2), (1000, 96, 2, 2, 0)]:\n"
+        "    planes = util.random_planes(rng, w, h, 3, hs, vs)\n"
+        "    img = util.make_image(w, h, planes, qts, hs, vs, cs, 0)\n"
+        "    assert np.array_equal(gpu.reconstruct([img])[0], oracle.reconstruct(img)), (w, h, hs, vs, cs)\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ZJ_SPC=str(spc))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_generic_kernel_still_matches():
+    """ZJ_NO_FAST routes everything through zj::reconstruct_kernel (the path SCALAR / unaligned images take)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "import oracle, util\n"
+        "from zune_jpeg_b200 import gpu\n"
+        "rng = np.random.default_rng(42)\n"
+        "qts = [util.std_qt(False), util.std_qt(True), util.std_qt(True)]\n"
+        "for (w, h, hs, vs, cs) in [(640, 480, 2, 2, 0), (333, 130, 1, 1, 0), (500, 330, 2, 1, 5), (256, 256, 1, 2, 2)]:\n"
+        "    planes = util.random_planes(rng, w, h, 3, hs, vs)\n"
+        "    img = util.make_image(w, h, planes, qts, hs, vs, cs, 0)\n"
+        "    assert np.array_equal(gpu.reconstruct([img])[0], oracle.reconstruct(img)), (w, h, hs, vs, cs)\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ZJ_NO_FAST="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_sparse_and_dense_blocks_mix():
+    """The rolled IDCT picks its short forms per warp: DC-only blocks, 4x4 blocks and dense blocks side by side."""
+    from zune_jpeg_b200 import gpu
+    rng = np.random.default_rng(43)
+    w, h = 1024, 128
+    for mode in MODES:
+        hs, vs = MODES[mode]
+        planes = util.random_planes(rng, w, h, 3, hs, vs)
+        for p in planes:
+            blk = p.reshape(-1, 64)
+            kind = rng.integers(0, 4, size=blk.shape[0])
+            blk[kind == 0, 1:] = 0                                   # DC only
+            m4 = np.ones(64, bool).reshape(8, 8); m4[:4, :4] = False
+            blk[np.ix_(kind == 1, m4.ravel())] = 0                   # top-left 4x4
+            m6 = np.ones(64, bool).reshape(8, 8); m6[:6, :] = False
+            blk[np.ix_(kind == 2, m6.ravel())] = 0                   # rows 6, 7 empty
+        img = util.make_image(w, h, planes, QTS, hs, vs, 0, 0)
+        want = oracle.reconstruct(img)
+        got = gpu.reconstruct([img])[0]
+        assert np.array_equal(got, want), mode

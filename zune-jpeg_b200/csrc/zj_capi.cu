@@ -187,6 +187,14 @@ static int check_buffers(const zj_image *img, const Plan &pl, const void *out, s
     return ZJ_OK;
 }
 
+// device-resident planes are read with 128-bit accesses: every plane must start on a 16-byte boundary
+static int check_device_alignment(const zj_image *img, const Plan &pl)
+{
+    for (uint32_t z = 0; z < pl.ncomp_used; z++)
+        if (reinterpret_cast<uintptr_t>(img->comp[z].coeff) & 15) return ZJ_ERR_INVALID_ARG;
+    return ZJ_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ batches
 struct zj_batch {
     int device;
@@ -259,6 +267,8 @@ int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *
         rc = plan_image(&imgs[i], &plans[i], out_dev[i]);
         if (rc) return rc;
         rc = check_buffers(&imgs[i], plans[i], out_dev[i], out_len[i]);
+        if (rc) return rc;
+        rc = check_device_alignment(&imgs[i], plans[i]);
         if (rc) return rc;
         for (int z = 0; z < 3; z++) plans[i].dev.coeff[z] = (uint32_t)z < plans[i].ncomp_used ? imgs[i].comp[z].coeff : nullptr;
         plans[i].dev.out = out_dev[i];

@@ -35,6 +35,9 @@
 #define ZF_LIKELY(x) (x)
 #define ZF_UNLIKELY(x) (x)
 #endif
+#ifndef ZF_WARP_ROTATE
+#define ZF_WARP_ROTATE 1
+#endif
 #ifndef ZF_EXPERIMENT_SKIPC
 #define ZF_EXPERIMENT_SKIPC 0   // timing experiment only (wrong chroma): skip the pass-1 IDCT
 #endif
@@ -844,7 +847,7 @@ reconstruct_kernel(const DevImage *__restrict__ images)
     constexpr int RPU = (MODE == MODE_V || MODE == MODE_HV) ? 2 : 1;   // rows per unit
     constexpr int NRU = ROWS / RPU;                                    // row groups per strip
     const int xunits = tw >> 3;
-    const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && (MODE != MODE_HV || hv_avx);
+    const bool fast_ok = (VARIANT == 0) && ((stride & 3u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (MODE != MODE_HV || hv_avx);
     // thread -> fixed x unit, loop over row groups: everything that depends only on the column is hoisted
     const float r_xu = __frcp_rn((float)xunits);
     const int rpp = div_small(ZJ_THREADS, r_xu);   // row groups per pass
@@ -1228,7 +1231,10 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         // 16-byte chunks XOR-swizzled by the slot number so that the per-thread 128-bit reads are conflict-free),
         // one strip ahead of the arithmetic.
         constexpr int NHB = FT::NSLOT * FT::CBR;                  // halo blocks per chroma plane
-        const int lane = tid & 31, wq = rtid >> 5;
+        // Which of the four producer jobs a hardware warp takes is rotated with the CTA index: the jobs are not equally heavy
+        // (in 4:2:0 two warps carry a luma AND a chroma pass), warp w always runs on SM sub-partition w mod 4, and the three
+        // resident CTAs of an SM would otherwise pile their heavy warps onto the same two sub-partitions.
+        const int lane = tid & 31, wq = ((rtid >> 5) + ZF_WARP_ROTATE * (int)(blockIdx.x + blockIdx.y + blockIdx.z)) & 3;
         const int ybpr = Wp >> 3;
         // block index -> plane, block row, global block column (-1: none), smem column
         auto decode = [&](int b, int &comp, int &br, int &gcol, int &lcol) {
@@ -1257,7 +1263,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
 #pragma unroll
         for (int ps = 0; ps < 2; ps++) {
             int comp, br, gcol, lcol;
-            decode(rtid + ps * ZF_PRODUCERS, comp, br, gcol, lcol);
+            decode(wq * 32 + lane + ps * ZF_PRODUCERS, comp, br, gcol, lcol);
             const bool active = gcol >= 0;
             pk[ps] = (comp == 0 ? (u32)(br * 8 * TWY + lcol) : (u32)(FT::YBYTES + (comp - 1) * FT::CBYTES + br * 8 * CS + lcol)) |
                      (active ? 0x10000u : 0u) | (comp ? 0x20000u : 0u) | ((u32)comp << 18);
