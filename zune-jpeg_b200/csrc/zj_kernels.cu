@@ -1263,11 +1263,15 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
 #pragma unroll
         for (int ps = 0; ps < 2; ps++) {
             int comp, br, gcol, lcol;
-            decode(wq * 32 + lane + ps * ZF_PRODUCERS, comp, br, gcol, lcol);
+            // pass 0: job wq.  Pass 1: the jobs after the first four, handed out so that a warp whose pass-0 job is a (cheap)
+            // chroma job gets one first -- without sub-sampling warps 0,1 transform luma and 2,3 take Cb, then Cr; in 4:2:2 the
+            // lone halo job goes to a chroma warp.  (4:2:0 / 4:4:0: all four pass-0 jobs are luma, order is irrelevant.)
+            const int jw = ps == 0 ? wq : ((wq + ((MODE == MODE_NONE || MODE == MODE_H) ? 2 : 0)) & 3);
+            decode(jw * 32 + lane + ps * ZF_PRODUCERS, comp, br, gcol, lcol);
             const bool active = gcol >= 0;
             pk[ps] = (comp == 0 ? (u32)(br * 8 * TWY + lcol) : (u32)(FT::YBYTES + (comp - 1) * FT::CBYTES + br * 8 * CS + lcol)) |
                      (active ? 0x10000u : 0u) | (comp ? 0x20000u : 0u) | ((u32)comp << 18);
-            const int B0 = ps * ZF_PRODUCERS + wq * 32;          // first block of the warp
+            const int B0 = ps * ZF_PRODUCERS + jw * 32;          // first block of the warp
             const int lsub = lane >> 3, lch = lane & 7;
             q0[ps] = q1[ps] = im.coeff[0];
             int mode = 0, lim0 = 0, lim1 = 0;
@@ -1391,9 +1395,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const int pbit = rgA & 1;                             // HV: row parity inside the double-row
     if (MODE == MODE_H) {
         off0 = first_x ? -CS : 0; off2 = last_x ? CS : 0;
-        // strip start (out[0], out[1] edge rule) and strip end (scalar.rs:46-57 / the SSE tail Q4b) stay generic
-        if (kind == 1 && first_x && rgA == 0) kindA = 2;
-        if (kind == 1 && last_x && rgA + NRG / 2 == NRG - 1) kindB = 2;
+        // the strip's first unit (out[0] = in[0], sse.rs:24-30) and last unit (the SSE tail, Q4b) are patched in place below
     } else if (MODE == MODE_HV) {
         off0 = (first_x && pbit) ? -CS : 0; off2 = last_x ? CS : 0;
         sel0 = (((pbit ? W : 0) + cc0) & 15) == 0;        // unit starts an AVX2 vector (else it ends one)
@@ -1455,9 +1457,20 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 } else if (MODE == MODE_H) {
                     const uint8_t *pa = base + ra * CS + lc;
                     const uint2 a = *reinterpret_cast<const uint2 *>(pa);
-                    const u32 hh = (u32)pa[off0 - 1] | ((u32)pa[off2 + 8] << 16);
+                    const bool hstart = first_x && rg == 0, hend = last_x && rg == NRG - 1;
+                    // strip start: out[0] = in[0] = T(in[0], in[0]) -- the left neighbour is the sample itself; no row above to read
+                    const u32 left = hstart ? (a.x & 0xffu) : (u32)pa[off0 - 1], right = hend ? 0u : (u32)pa[off2 + 8];
                     const u32 r[4] = {lanes01(a.x), lanes23(a.x), lanes01(a.y), lanes23(a.y)};
-                    hfilter16(hh, r, E0[c], O0[c]);
+                    hfilter16(left | (right << 16), r, E0[c], O0[c]);
+                    if (ZF_UNLIKELY(hend)) {
+                        // the last eight outputs of the strip, as upsample_horizontal_sse leaves them (sse.rs:117-131, Q4b), R = in[n-8..n-1]:
+                        //   out[8..15] = T(R4,R3), T(R4,R5), T(R5,R4), R5, R6, T(R6,R5), T(R6,R7), R7
+                        // against the regular T(R4,R3), T(R4,R5), T(R5,R4), T(R5,R6), T(R6,R5), T(R6,R7), T(R7,R6), T(R7,R8)
+                        const u32 e3 = E0[c][3], o3 = O0[c][3];                       // (out12, out14), (out13, out15) regular
+                        O0[c][2] = prmt(O0[c][2], r[2], 0x7610u);                     // out11 = R5
+                        E0[c][3] = prmt(r[3], o3, 0x5410u);                           // (R6, T(R6,R7))
+                        O0[c][3] = prmt(e3, r[3], 0x7610u);                           // (T(R6,R5), R7)
+                    }
                 } else if (ZF_LIKELY(!hv_tail)) {
                     const uint8_t *pa = base + ra * CS + lc, *pb = base + rb * CS + lc;
                     const uint2 a = *reinterpret_cast<const uint2 *>(pa), b = *reinterpret_cast<const uint2 *>(pb);
