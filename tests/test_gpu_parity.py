@@ -234,3 +234,16 @@ def test_sparse_and_dense_blocks_mix():
         want = oracle.reconstruct(img)
         got = gpu.reconstruct([img])[0]
         assert np.array_equal(got, want), mode
+
+
+def test_gray_fast_kernel_corners():
+    """Luma-only output through gray_fast_kernel: odd block-row counts, ragged widths, colour inputs of every sub-sampling,
+    unaligned output pointers."""
+    rng = np.random.default_rng(51)
+    for (w, h) in [(520, 24), (1001, 77), (33, 9), (2056, 40), (512, 16), (528, 8), (5000, 72)]:
+        assert _run_case(rng, w, h, "444", 1, 0, n_comp=1) in ("ok", "panic")
+        for mode in MODES:
+            assert _run_case(rng, w, h, mode, 1, 0) in ("ok", "panic")
+    for off in (0, 1, 4, 16):
+        got, want = _device_case(rng, 640, 56, "420", 1, out_offset=off)
+        assert np.array_equal(got, want), off

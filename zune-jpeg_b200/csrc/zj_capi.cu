@@ -49,7 +49,7 @@ struct Plan {
     size_t chunk[3];   // i16 per strip per component
     size_t out_size;
     DevImage dev;      // pointers filled by the caller
-    uint32_t grid_tiles;
+    uint32_t grid_tiles, grid_strips;   // launch extents (grid_strips: strips as the kernel counts them)
 };
 
 // Strip geometry of reference src/mcu.rs:139-226 (baseline) / src/mcu_prog.rs:132-203 (progressive) and the
@@ -100,6 +100,7 @@ static int plan_image(const zj_image *img, Plan *pl, const void *out = nullptr)
         else return ZJ_ERR_REF_PANIC;                                      // mcu.rs:354, chunks.next().unwrap()
     }
     pl->n_strips = n_strips;
+    pl->grid_strips = n_strips;
     pl->rows = rows;
     pl->out_size = (size_t)w * hh * nc;
     pl->chunk[0] = (size_t)ybr * h * mcu_x * 64;
@@ -133,9 +134,20 @@ static int plan_image(const zj_image *img, Plan *pl, const void *out = nullptr)
         // ycbcr_to_grayscale (color_convert/scalar.rs:97-112): width_mcu = len / width must equal the strip's row
         // count, otherwise the chunking overruns the strip's output slice and the reference panics (Q7).
         const size_t len = (size_t)rows * d.Wp;
-        if (len / w != rows) return ZJ_ERR_REF_PANIC;
+        if (n_strips > 0 && len / w != rows) return ZJ_ERR_REF_PANIC;   // (no strip, no call, no panic: the output stays zero)
         d.gray_rows_ok = 1;
-        d.n_tiles = (d.Wp / 8 + ZJ_THREADS - 1) / ZJ_THREADS;
+        d.gray_brows = n_strips * (rows / 8);
+        // X86 variant: producer / consumer kernel over pairs of block rows; SCALAR (unclamped DC-only samples): gray_kernel
+        pl->fast = img->variant == ZJ_VARIANT_X86 && !getenv("ZJ_NO_FAST");
+        if (pl->fast) {
+            const uint32_t ucols = (d.Wp + 15) / 16;
+            d.n_tiles = (ucols + ZF_XU_GRAY - 1) / ZF_XU_GRAY;
+            d.tile_q = ucols / d.n_tiles;
+            d.tile_r = ucols % d.n_tiles;
+            pl->grid_strips = (d.gray_brows + 1) / 2;
+        } else {
+            d.n_tiles = (d.Wp / 8 + ZJ_THREADS - 1) / ZJ_THREADS;
+        }
         pl->grid_tiles = d.n_tiles;
     } else if (kind == OUT_YCC) {
         d.n_norm = w; d.P = 3 * w;
@@ -297,7 +309,7 @@ int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *
         g.first = (uint32_t)k;
         while (e < order.size() && key(order[e]) == key(order[k]) && e - k < 65535) {
             g.max_tiles = std::max(g.max_tiles, plans[order[e]].grid_tiles);
-            g.max_strips = std::max(g.max_strips, plans[order[e]].n_strips);
+            g.max_strips = std::max(g.max_strips, plans[order[e]].grid_strips);
             e++;
         }
         g.count = (uint32_t)(e - k);

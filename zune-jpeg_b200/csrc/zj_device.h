@@ -44,6 +44,7 @@ constexpr int ZF_THREADS = 256, ZF_PRODUCERS = 128, ZF_CONSUMERS = 128;
 constexpr int ZF_MINBLOCKS = ZF_CFG_MINBLOCKS;
 constexpr int ZF_DEFAULT_SPC = ZF_CFG_SPC;      // strips per CTA
 // unit columns (16 luma samples) per tile: 2 * ZF_CONSUMERS / row groups per strip
+constexpr int ZF_XU_GRAY = 32;                  // luma-only fast kernel: 512-sample tiles
 constexpr int ZF_XU_NONE = 2 * ZF_CONSUMERS / 8, ZF_XU_H = 2 * ZF_CONSUMERS / 16, ZF_XU_V = 2 * ZF_CONSUMERS / 8, ZF_XU_HV = 2 * ZF_CONSUMERS / 16;
 
 struct DevImage {
@@ -66,6 +67,7 @@ struct DevImage {
     uint32_t small_width;     // width < 16: temp-buffer path (worker.rs:158-163,176-198)
     uint32_t hv_avx;          // HV + X86 + chroma strip >= 500 samples -> AVX2 closed form
     uint32_t gray_rows_ok;    // Q7 resolved: 1 = plain row copy is what the reference does
+    uint32_t gray_brows;      // luma-only output: block rows of the Y plane the reference processes
     uint32_t tile_q, tile_r;  // tile t covers MCU columns (fast kernel: 16-sample unit columns) [t*q + min(t,r), ...): the first r tiles are one wider
     uint64_t magic_w;         // ceil(2^40 / W): idx / W == (idx * magic_w) >> 40 for idx < 2^20
 };

@@ -1652,6 +1652,127 @@ static cudaError_t launch_reconstruct(const DevImage *d_images, const LaunchGrou
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------- luma-only kernel, fast variant
+// (YCbCr | GRAYSCALE) -> GRAYSCALE for the X86 variant, built from the same parts as reconstruct_fast_kernel: four
+// producer warps stage coefficients with cp.async and run the rolled IDCT into double-buffered sample planes, four
+// consumer warps copy the planes out in 16-byte row segments.  A CTA owns one tile column (up to 512 samples) of `spc`
+// consecutive "strips" of TWO luma block rows (16 image rows; 128 blocks = one IDCT pass).  The plane is just a raster of
+// blocks here -- the reference's strip geometry only decides how many block rows exist (DevImage::gray_brows).
+constexpr int ZG_TW = 512, ZG_ROWS = 16, ZG_BUF = ZG_TW * ZG_ROWS;   // tile width, rows per strip, bytes per plane buffer
+
+__global__ void __launch_bounds__(ZF_THREADS, 3)
+gray_fast_kernel(const DevImage *__restrict__ images, const int spc)
+{
+    extern __shared__ __align__(128) uint8_t sDynAll[];  // [staging 16 KB | scratch 32 KB | zero slot | 2 plane buffers]
+    uint8_t *const sPlanes = sDynAll + 3 * ZF_PRODUCERS * 128 + 128;
+    __shared__ __align__(16) u32 sQ[32];
+
+    const DevImage &im = images[blockIdx.z];
+    const u32 tile = blockIdx.x;
+    if (tile >= im.n_tiles) return;
+    const int tid = threadIdx.x;
+    const u32 stride = im.stride, width = im.width, height = im.height;
+    uint8_t *__restrict__ out = im.out;
+    const u32 brows = im.gray_brows;                       // luma block rows the reference processes
+    const u32 n_strips = (brows + 1) / 2;
+    const u32 s_begin = blockIdx.y * (u32)spc;
+    if (s_begin >= n_strips) {
+        // rows below the processed block rows stay zero (Q1); written by the first row of CTAs past the image's strips
+        if (s_begin >= n_strips + (u32)spc) return;
+        const size_t lo = (size_t)min(brows * 8u, height) * stride, hi = (size_t)height * stride;
+        if (lo >= hi) return;
+        const size_t span = hi - lo, per = (span + im.n_tiles - 1) / im.n_tiles;
+        size_t b0 = lo + (size_t)tile * per, b1 = b0 + per;
+        if (b1 > hi) b1 = hi;
+        for (size_t b = b0 + tid; b < b1; b += ZF_THREADS) out[b] = 0;
+        return;
+    }
+    const int n_it = (int)(min(s_begin + (u32)spc, n_strips) - s_begin);
+    const int u0 = (int)(tile * im.tile_q + min(tile, im.tile_r)), u1 = (int)((tile + 1) * im.tile_q + min(tile + 1, im.tile_r));
+    const int Wp = (int)im.Wp, ybpr = Wp >> 3;
+    const int X0 = 16 * u0, yb0 = 2 * u0, nyb = min(2 * u1, ybpr) - yb0;   // luma block columns of the tile
+    if (tid < 32) sQ[tid] = im.qtw[0][tid];
+    __syncthreads();
+
+    if (tid < ZF_PRODUCERS) {
+        const int lane = tid & 31, wq = tid >> 5;
+        const int br = wq >> 1, bc0 = (wq & 1) * 32;         // the warp's block row inside the strip, first block column
+        const bool active = bc0 + lane < nyb;
+        const bool work = bc0 < nyb;
+        const u32 dsto = (u32)(br * 8 * ZG_TW + (bc0 + lane) * 8);
+        const u32 step = (u32)(2 * ybpr * 64);                // i16 per strip
+        const int16_t *q0 = im.coeff[0] + (((size_t)s_begin * 2 + br) * ybpr + yb0 + bc0) * 64 + (lane >> 3) * 64 + (lane & 7) * 8;
+        u32 jm = 0;                                            // bit k: chunk k of the cooperative copy is inside the run
+        for (int k = 0; k < 8; k++) if (4 * k + (lane >> 3) < min(max(nyb - bc0, 0), 32)) jm |= 1u << k;
+        const u32 stage0 = (u32)__cvta_generic_to_shared(sDynAll) + (u32)(wq * 32) * 128u;
+        const u32 d_even = stage0 + (u32)(lane >> 3) * 128u + (u32)(((lane & 7) ^ (lane >> 3)) * 16);
+        const u32 d_odd = stage0 + (u32)(lane >> 3) * 128u + (u32)(((lane & 7) ^ ((lane >> 3) + 4)) * 16);
+        const u32 slx = (stage0 + (u32)lane * 128u) | (u32)((lane & 7) * 16);
+        const u32 scr = (u32)__cvta_generic_to_shared(sDynAll) + ZF_PRODUCERS * 128u + (u32)tid * 16u;
+        const u32 zslot = ((u32)__cvta_generic_to_shared(sDynAll) + 3u * ZF_PRODUCERS * 128u) | (u32)((lane & 7) * 16);
+        if (tid < 8) sts128(zslot - (u32)((lane & 7) * 16) + (u32)tid * 16u, 0u, 0u, 0u, 0u);
+        asm volatile("bar.sync %0, %1;" ::"r"(6), "n"(ZF_PRODUCERS) : "memory");   // producers only
+        auto issue = [&](const int16_t *g, const bool valid) {
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (jm & (1u << k))
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(((k & 1) ? d_odd : d_even) + k * 512u), "l"(g + k * 256) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // the last strip of an image with an odd number of block rows has no second block row: nothing to read there
+        auto row_exists = [&](int it) { return (s_begin + (u32)it) * 2 + (u32)br < brows; };
+        issue(q0, row_exists(0));
+        q0 += step;
+        for (int it = 0; it < n_it; it++) {
+            uint8_t *planes = sPlanes + (it & 1) * ZG_BUF;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            if (it >= 2) bar_sync(BAR_EMPTY + (it & 1));
+            auto refill = [&]() {
+                if (it + 1 < n_it) { issue(q0, row_exists(it + 1)); q0 += step; }
+            };
+            if (work && row_exists(it)) idct_rolled(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, refill);
+            else refill();
+            bar_arrive(BAR_FULL + (it & 1));
+        }
+        return;
+    }
+
+    // consumers: four 16-sample units per thread and strip (rows rg, rg+4, rg+8, rg+12 of the strip)
+    const int tc = tid - ZF_PRODUCERS;
+    const int xu = tc & 31, rgA = tc >> 5;
+    const int xs = X0 + 16 * xu, xl = 16 * xu;
+    const int npx = (u0 + xu < u1) ? min(max((int)width - xs, 0), 16) : 0;     // samples of the unit inside the image row
+    const bool vec = npx == 16 && (stride & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const bool words = npx == 16 && (stride & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    for (int it = 0; it < n_it; it++) {
+        const uint8_t *planes = sPlanes + (it & 1) * ZG_BUF;
+        const u32 y_base = (s_begin + (u32)it) * ZG_ROWS;
+        bar_sync(BAR_FULL + (it & 1));
+        if (npx > 0) {
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                const int rg = rgA + 4 * h;
+                const u32 y = y_base + (u32)rg;
+                if (y >= height) continue;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (y < brows * 8u) v = *reinterpret_cast<const uint4 *>(planes + rg * ZG_TW + xl);   // `as u8` row copy (scalar.rs:91-114)
+                uint8_t *d = out + (size_t)y * stride + xs;
+                if (vec) *reinterpret_cast<uint4 *>(d) = v;
+                else if (words) { u32 *dw = reinterpret_cast<u32 *>(d); dw[0] = v.x; dw[1] = v.y; dw[2] = v.z; dw[3] = v.w; }
+                else {
+                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 16; k++) if (k < npx) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+                }
+            }
+        }
+        if (it + 2 < n_it) bar_arrive(BAR_EMPTY + (it & 1));
+    }
+}
+
 static int g_spc = 0;  // strips per CTA of the fast kernel (0 = default; ZJ_SPC in the environment overrides)
 
 template <int MODE>
@@ -1678,8 +1799,30 @@ static cudaError_t launch_fast(const DevImage *d_images, const LaunchGroup &g, c
     return cudaGetLastError();
 }
 
+static cudaError_t launch_gray_fast(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
+{
+    if (g_spc == 0) {
+        const char *e = getenv("ZJ_SPC");
+        g_spc = e ? atoi(e) : ZF_DEFAULT_SPC;
+        if (g_spc < 1) g_spc = 1;
+    }
+    dim3 grid(g.max_tiles, (g.max_strips + g_spc - 1) / g_spc + 1, g.count);   // max_strips: pairs of block rows
+    constexpr size_t smem = 3 * ZF_PRODUCERS * 128 + 128 + 2 * ZG_BUF;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gray_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    gray_fast_kernel<<<grid, ZF_THREADS, smem, stream>>>(d_images + g.first, g_spc);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_group(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
 {
+    if (g.gray && g.fast) return launch_gray_fast(d_images, g, stream);
     if (g.fast) {
         switch (g.mode) {
         case MODE_NONE: return launch_fast<MODE_NONE>(d_images, g, stream);
