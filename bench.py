@@ -71,7 +71,7 @@ def make_pool(cfg: str, n_distinct: int, rank: int):
         data = jpeg_util.synth_jpeg(1000 * rank + i, w, h, sub, 90, prog, gray, restart_rows=1 if cfg == "c5" else 0)
         d = Decoder.new_with_options(ZuneJpegOptions().set_out_colorspace(ColorSpace(out_cs)))
         img, planes = d.decode_coefficients(data)
-        return img, planes, len(data)
+        return img, planes, data
 
     with ThreadPoolExecutor(max_workers=min(n_distinct, host_threads())) as ex:
         return list(ex.map(one, range(n_distinct)))
@@ -123,7 +123,7 @@ def time_cpu_port(pool, seconds: float, threads: int):
     """oracle (X86 variant) strip-parallel on `threads` host threads; returns (MP/s, n images timed)."""
     import oracle
     imgs = []
-    for (img, planes, _) in pool:
+    for (img, planes, _jpeg) in pool:
         for z in range(img.n_comp):
             img.comp[z].coeff = planes[z].ctypes.data
         imgs.append(img)
@@ -153,7 +153,7 @@ def run_reference(args):
     pool = make_pool(cfg, n_sample, 0)
     import oracle
     imgs = []
-    for (img, planes, _) in pool:
+    for (img, planes, _jpeg) in pool:
         for z in range(img.n_comp):
             img.comp[z].coeff = planes[z].ctypes.data
         imgs.append(img)
@@ -270,7 +270,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         pinned_planes = []
-        for (img, planes, _) in pool:
+        for (img, planes, _jpeg) in pool:
             row = []
             for p in planes:
                 if p.nbytes:
@@ -328,6 +328,57 @@ def run_ours(args):
         cpu = {"value": round(v, 2), "unit": "MP/s", "cores": threads, "kind": "port",
                "sample": f"{n} images ({n_distinct} distinct {w}x{h}, repeated for >= {args.cpu_seconds:.0f} s), planes in RAM -> pixels in RAM, oracle X86 variant, strip-parallel"}
 
+    # ---- whole decode (SURVEY 8(f) "next" row, informational): JPEG bytes -> pixels through zj_decode_batch, i.e. the
+    # host threads entropy-decode different images while the GPU reconstructs the finished ones; beside it the CPU-only
+    # equivalent (host stage + oracle path, one image per thread).  Rank 0, N=1 only.
+    decode = None
+    if rank == 0 and world == 1 and not args.no_decode:
+        from concurrent.futures import ThreadPoolExecutor
+        from zune_jpeg_b200.decoder import ColorSpace, Decoder, ZuneJpegOptions, decode_batch
+        threads = host_threads()
+        nd = min(batch, args.decode_images)
+        jpegs = [pool[b % n_distinct][2] for b in range(nd)]
+        opts = ZuneJpegOptions().set_out_colorspace(ColorSpace(out_cs))
+        pinned_dec = gpu.PinnedBuffer(out_bytes * nd)
+        outs = [pinned_dec.array[b * out_bytes:(b + 1) * out_bytes] for b in range(nd)]
+        decode_batch(jpegs[:threads], opts, threads=threads, out=outs[:threads])      # warm-up: decoders' pinned planes, pools
+        t0 = time.perf_counter()
+        res = decode_batch(jpegs, opts, threads=threads, out=outs)
+        dt = time.perf_counter() - t0
+        if any(not isinstance(r, int) for r in res):
+            raise SystemExit(f"bench.py: zj_decode_batch failed: {[r for r in res if not isinstance(r, int)][:1]}")
+        if not args.no_check and not np.array_equal(outs[0], want):
+            raise SystemExit("bench.py: zj_decode_batch output differs from the oracle")
+        decode = {"value": round(nd * w * h / 1e6 / dt, 2), "unit": "MP/s", "threads": threads, "images": nd,
+                  "jpeg_bytes": int(sum(len(j) for j in jpegs)), "seconds": round(dt, 3),
+                  "how": "zj_decode_batch: JPEG bytes in host memory -> pixels in pinned host memory (headers + Huffman on the host threads, the rest on the GPU)"}
+        if not args.no_cpu:
+            import oracle
+
+            import threading
+            from zune_jpeg_b200 import _ffi
+            lib = _ffi.load()
+            tls = threading.local()
+
+            def cpu_one(j):
+                # one decoder per worker thread (its planes are reused), descriptor points straight at them: no copies in Python
+                if not hasattr(tls, "d"):
+                    tls.d = Decoder.new_with_options(opts)
+                img = ZjImage()
+                rc = lib.zj_decoder_decode_coefficients(tls.d._h, j, len(j), C.byref(img))
+                if rc != 0:
+                    raise SystemExit(f"host stage failed: {rc}")
+                return len(oracle.reconstruct(img, threads=1))
+
+            nc = min(nd, 4 * threads)
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                list(ex.map(cpu_one, jpegs[:threads]))
+                t0 = time.perf_counter()
+                list(ex.map(cpu_one, jpegs[:nc]))
+                dtc = time.perf_counter() - t0
+            decode["cpu"] = {"value": round(nc * w * h / 1e6 / dtc, 2), "unit": "MP/s", "threads": threads, "images": nc,
+                             "how": "the same host stage + the oracle port of the pixel path, one image per thread"}
+
     # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
     peaks = {}
     try:
@@ -356,7 +407,7 @@ def run_ours(args):
                        "variant": "X86 (use_unsafe=true)", "bytes_per_px": B_PER_PX[cfg],
                        "l2": f"inputs {algo_bytes / 1e9:.2f} GB per step per GPU, far larger than the 126 MB L2 (no flush needed)",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode": decode, "clocks": clocks,
             "checked_vs_oracle": check, "setup_s": round(time.perf_counter() - t_setup, 1),
         }
         print(json.dumps(line))
@@ -376,6 +427,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the whole-decode (JPEG bytes -> pixels) measurement")
+    ap.add_argument("--decode-images", type=int, default=128)
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

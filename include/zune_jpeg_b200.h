@@ -218,6 +218,14 @@ ZJ_API int zj_decoder_decode_coefficients(zj_decoder *d, const uint8_t *buf, siz
 ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out,
                                     size_t *out_len);
 ZJ_API void zj_buffer_free(uint8_t *p);
+/* Batch front door (the reference has none: it parallelises the strips of ONE image, mcu.rs:230-369): n JPEGs are
+ * decoded by `o->num_threads` host threads (0 = one per hardware thread), one image per thread at a time; each thread
+ * runs the host stage and hands its planes to zj_gpu_reconstruct, so entropy decoding of some images overlaps transfer
+ * and reconstruction of others.  out[i] non-NULL on entry = caller buffer of out_len[i] bytes (pinned memory copies
+ * fastest); NULL = malloc'ed here (zj_buffer_free).  status[i] = per-image zj_status; returns the number of failed
+ * images (0 = all decoded) or a negative zj_status for invalid arguments. */
+ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                           uint8_t **out, size_t *out_len, int *status);
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d);                 /* zj_decode_error_kind                */
 ZJ_API const char *zj_decoder_error(const zj_decoder *d);              /* Display text of the DecodeErrors    */
 

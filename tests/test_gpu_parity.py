@@ -247,3 +247,42 @@ def test_gray_fast_kernel_corners():
     for off in (0, 1, 4, 16):
         got, want = _device_case(rng, 640, 56, "420", 1, out_offset=off)
         assert np.array_equal(got, want), off
+
+
+def test_decode_batch_matches_single_image_decodes():
+    """zj_decode_batch (host threads entropy-decode different images while the GPU reconstructs finished ones) returns exactly
+    what one Decoder per image returns, in input order, with per-image errors."""
+    import json
+    import os
+    import jpeg_util
+    from zune_jpeg_b200.decoder import ColorSpace, DecodeErrors, Decoder, ZuneJpegOptions, decode_batch
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    man = json.load(open(os.path.join(golden, "manifest.json")))
+    rgb = [c for c in man["cases"] if c["out"] == "RGB" and c["variant"] == "X86"]
+    jpegs = [open(os.path.join(golden, c["jpeg"]), "rb").read() for c in rgb]
+    wants = [np.fromfile(os.path.join(golden, c["pixels"]), np.uint8).tobytes() for c in rgb]
+    for i in range(6):   # a few bigger ones: 4:2:0, 4:4:4, 4:2:2 progressive, grayscale
+        sub, prog, gray = [("420", False, False), ("444", False, False), ("422", True, False), ("444", False, True)][i % 4]
+        jpegs.append(jpeg_util.synth_jpeg(100 + i, 640 + 16 * i, 360 + 8 * i, sub, 90, prog, gray))
+        wants.append(Decoder.new().decode_buffer(jpegs[-1]))
+    bad = bytes([0xff, 0xd8, 0xa4])
+    batch = jpegs[:3] + [bad] + jpegs[3:] + jpegs   # every image twice, one broken stream in between
+    res = decode_batch(batch, threads=5)
+    expect = wants[:3] + [None] + wants[3:] + wants
+    assert len(res) == len(expect)
+    for r, w in zip(res, expect):
+        if w is None:
+            assert isinstance(r, DecodeErrors) and r.status == -9
+        else:
+            assert r == w
+    # caller-provided (pinned) output buffers, non-default options
+    from zune_jpeg_b200 import gpu
+    opts = ZuneJpegOptions().set_out_colorspace(ColorSpace.RGBA)
+    sizes = [len(Decoder.new_with_options(opts).decode_buffer(j)) for j in jpegs]
+    pinned = gpu.PinnedBuffer(sum(sizes))
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    outs = [pinned.array[offs[i]:offs[i + 1]] for i in range(len(jpegs))]
+    res = decode_batch(jpegs, opts, threads=0, out=outs)
+    assert res == sizes
+    for j, o in zip(jpegs, outs):
+        assert o.tobytes() == Decoder.new_with_options(opts).decode_buffer(j)

@@ -152,3 +152,18 @@ def test_golden_fixtures():
         _, _, out = _oracle_pixels(data, ColorSpace[case["out"]], case["variant"] == "X86")
         want = np.fromfile(os.path.join(GOLDEN, case["pixels"]), np.uint8)
         assert np.array_equal(out, want), case["jpeg"]
+
+
+def test_decode_batch_without_a_device():
+    """zj_decode_batch on a machine without a GPU: the host stage still runs per image (decode errors are reported as such),
+    the pixel stage reports ZJ_ERR_NO_DEVICE -- never a CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a CUDA device")
+    from zune_jpeg_b200.decoder import decode_batch
+    good = open(os.path.join(GOLDEN, "c420_base.jpg"), "rb").read()
+    res = decode_batch([good, bytes([0xff, 0xd8, 0xa4]), good], threads=2)
+    assert len(res) == 3 and all(isinstance(r, DecodeErrors) for r in res)
+    assert res[0].status == -6 and res[2].status == -6      # ZJ_ERR_NO_DEVICE
+    assert res[1].status == -9                                # ZJ_ERR_DECODE
+    assert decode_batch([]) == []

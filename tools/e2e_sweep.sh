@@ -2,7 +2,7 @@
 # tools/e2e_sweep.sh "streams:budgetMB ..." -- end-to-end (host buffers) bench for staging configurations (run on the GPU box)
 for it in $1; do
   s=${it%%:*}; b=${it##*:}
-  ZJ_E2E_STREAMS=$s ZJ_E2E_BUDGET_MB=$b python bench.py --no-cpu --no-check --steps 3 --warmup 3 > gpurun_out/e2e_${s}_$b.json 2> gpurun_out/e2e_${s}_$b.err
+  ZJ_E2E_STREAMS=$s ZJ_E2E_BUDGET_MB=$b python bench.py --no-cpu --no-decode --no-check --steps 3 --warmup 3 > gpurun_out/e2e_${s}_$b.json 2> gpurun_out/e2e_${s}_$b.err
   python - <<PY
 import json
 try:

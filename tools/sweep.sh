@@ -3,7 +3,7 @@
 tag=$1; shift; list=$1; shift
 for it in $list; do
   v=${it%%:*}; s=${it##*:}
-  ZJ_LIB_PATH=build/variants/libzj_$v.so ZJ_SPC=$s python bench.py --no-e2e --no-cpu --steps 10 "$@" > gpurun_out/${tag}_${v}_$s.json 2> gpurun_out/${tag}_${v}_$s.err
+  ZJ_LIB_PATH=build/variants/libzj_$v.so ZJ_SPC=$s python bench.py --no-e2e --no-cpu --no-decode --steps 10 "$@" > gpurun_out/${tag}_${v}_$s.json 2> gpurun_out/${tag}_${v}_$s.err
   python - <<PY
 import json
 try:

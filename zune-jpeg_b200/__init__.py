@@ -5,11 +5,11 @@ from ._ffi import (  # noqa: F401
     VARIANT_SCALAR, VARIANT_X86, ZjComponent, ZjImage, ZjImageInfo, ZjOptions,
 )
 
-__all__ = ["Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "reconstruct"]
+__all__ = ["Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "reconstruct", "decode_batch"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require the built library
-    if name in ("Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "UnsupportedSchemes"):
+    if name in ("Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "UnsupportedSchemes", "decode_batch"):
         from . import decoder as _d
         return getattr(_d, name)
     if name in ("reconstruct", "Batch", "DeviceBuffer", "PinnedBuffer", "make_image"):

@@ -110,6 +110,8 @@ SYMBOLS = {
     "zj_decoder_decode_coefficients": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(ZjImage)]),
     "zj_decoder_decode_buffer": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]),
     "zj_buffer_free": (None, [_P]),
+    "zj_decode_batch": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
+                                  C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "zj_decoder_error_kind": (C.c_int, [_P]),
     "zj_decoder_error": (C.c_char_p, [_P]),
 }

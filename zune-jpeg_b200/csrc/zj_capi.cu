@@ -215,6 +215,8 @@ struct zj_batch {
     DevImage *d_images;
     size_t n_images;
     uint64_t algo_bytes;
+    cudaStream_t pool_stream;   // non-null + pooled: descriptors come from the stream-ordered pool of this stream
+    bool pooled;
 };
 
 static int set_device(int device)
@@ -267,7 +269,18 @@ int zj_validate_image(const zj_image *img)
     return ZJ_OK;
 }
 
+// `pooled`: allocate / upload the descriptors in stream order on `ps` (no device-wide synchronisation: cudaMalloc and
+// above all cudaFree serialise every thread that feeds the device, which is what zj_decode_batch's workers are)
+static int batch_create_impl(int device, const zj_image *imgs, size_t n, uint8_t *const *out_dev, const size_t *out_len, zj_batch **plan,
+                             bool pooled, cudaStream_t ps);
+
 int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *out_dev, const size_t *out_len, zj_batch **plan)
+{
+    return batch_create_impl(device, imgs, n, out_dev, out_len, plan, false, nullptr);
+}
+
+static int batch_create_impl(int device, const zj_image *imgs, size_t n, uint8_t *const *out_dev, const size_t *out_len, zj_batch **plan,
+                             bool pooled, cudaStream_t ps)
 {
     if (!plan) return ZJ_ERR_INVALID_ARG;
     *plan = nullptr;
@@ -317,12 +330,17 @@ int zj_batch_create(int device, const zj_image *imgs, size_t n, uint8_t *const *
         k = e;
     }
     if (!host.empty()) {
-        cudaError_t e = cudaMalloc(&b->d_images, host.size() * sizeof(DevImage));
+        cudaError_t e = pooled ? cudaMallocAsync((void **)&b->d_images, host.size() * sizeof(DevImage), ps)
+                               : cudaMalloc(&b->d_images, host.size() * sizeof(DevImage));
         if (e != cudaSuccess) { delete b; return cuda_fail(e, "cudaMalloc(descriptors)"); }
-        e = cudaMemcpy(b->d_images, host.data(), host.size() * sizeof(DevImage), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFree(b->d_images); delete b; return cuda_fail(e, "cudaMemcpy(descriptors)"); }
+        // (pageable source: the async copy returns once the data sits in the driver's staging buffer)
+        e = pooled ? cudaMemcpyAsync(b->d_images, host.data(), host.size() * sizeof(DevImage), cudaMemcpyHostToDevice, ps)
+                   : cudaMemcpy(b->d_images, host.data(), host.size() * sizeof(DevImage), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { if (pooled) cudaFreeAsync(b->d_images, ps); else cudaFree(b->d_images); delete b; return cuda_fail(e, "cudaMemcpy(descriptors)"); }
         b->n_images = host.size();
     }
+    b->pooled = pooled;
+    b->pool_stream = ps;
     *plan = b;
     return ZJ_OK;
 }
@@ -347,7 +365,10 @@ uint64_t zj_batch_algorithmic_bytes(const zj_batch *b) { return b ? b->algo_byte
 void zj_batch_destroy(zj_batch *b)
 {
     if (!b) return;
-    if (b->d_images) { cudaSetDevice(b->device); cudaFree(b->d_images); }
+    if (b->d_images) {
+        cudaSetDevice(b->device);
+        if (b->pooled) cudaFreeAsync(b->d_images, b->pool_stream); else cudaFree(b->d_images);
+    }
     delete b;
 }
 
@@ -382,7 +403,15 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
     const char *env_ns = getenv("ZJ_E2E_STREAMS"), *env_mb = getenv("ZJ_E2E_BUDGET_MB");
     const int NS = std::max(1, std::min(NS_MAX, env_ns ? atoi(env_ns) : 3));
     cudaStream_t st[NS_MAX];
-    for (int k = 0; k < NS; k++) CU(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+    // the staging streams are created once per host thread and device and reused: creating / destroying streams takes
+    // driver-wide locks, which hurts when many threads call in (zj_decode_batch)
+    struct StreamCache { cudaStream_t s[64][NS_MAX] = {}; };
+    thread_local StreamCache cache;
+    if (device >= 64) return ZJ_ERR_NO_DEVICE;
+    for (int k = 0; k < NS; k++) {
+        if (!cache.s[device][k]) CU(cudaStreamCreateWithFlags(&cache.s[device][k], cudaStreamNonBlocking));
+        st[k] = cache.s[device][k];
+    }
     // everything issued on `user` before this call must be visible
     cudaEvent_t ev_in;
     CU(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
@@ -428,7 +457,7 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
         }
         if (rc != ZJ_OK) break;
         zj_batch *b = nullptr;
-        rc = zj_batch_create(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b);
+        rc = batch_create_impl(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b, true, s);
         if (rc != ZJ_OK) break;
         batches.push_back(b);
         rc = zj_batch_run(b, s);
@@ -447,7 +476,6 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
     }
     for (void *p : to_free) cudaFree(p);
     for (zj_batch *b : batches) zj_batch_destroy(b);
-    for (int k = 0; k < NS; k++) cudaStreamDestroy(st[k]);
     cudaEventDestroy(ev_in);
     if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize(user); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(user)"); }
     return rc;

@@ -17,6 +17,9 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/zune_jpeg_b200.h"
@@ -1191,6 +1194,70 @@ ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t le
     return ZJ_OK;
 }
 ZJ_API void zj_buffer_free(uint8_t *p) { free(p); }
+
+// Batch front door.  The reference decodes one image per Decoder and parallelises the strips of that image
+// (scoped_threadpool, mcu.rs:230-369); with the pixel path on the GPU the host threads are free to run the branchy
+// stage of DIFFERENT images side by side: every worker owns a decoder (its pinned coefficient planes are reused from
+// image to image), entropy-decodes one image, hands the planes to zj_gpu_reconstruct on its own streams and moves on,
+// so the Huffman stage of some images overlaps transfer and reconstruction of others.
+ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                           uint8_t **out, size_t *out_len, int *status)
+{
+    if ((!bufs || !lens || !out || !out_len || !status) && n) return ZJ_ERR_INVALID_ARG;
+    zj_options opt;
+    if (o) opt = *o; else zj_options_default(&opt);
+    size_t nthreads = opt.num_threads ? opt.num_threads : std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    if (nthreads > n) nthreads = n;
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    // decoders (with their pinned coefficient planes) are kept between calls: page-locking and releasing 25 MB per
+    // image and thread costs more than decoding it, and both serialise in the driver
+    static std::mutex idle_mu;
+    static std::vector<zj_decoder *> idle;
+    auto worker = [&]() {
+        zj_decoder *d = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(idle_mu);
+            if (!idle.empty()) { d = idle.back(); idle.pop_back(); }
+        }
+        if (d) { d->options = opt; d->user_out_cs = opt.out_colorspace; d->clear_error(); }
+        else d = zj_decoder_new(&opt);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            if (!d) { status[i] = ZJ_ERR_OOM; failed++; continue; }
+            zj_image img;
+            int rc = (!bufs[i] && lens[i]) ? ZJ_ERR_INVALID_ARG : zj_decoder_decode_coefficients(d, bufs[i], lens[i], &img);
+            size_t need = 0;
+            if (rc == ZJ_OK) {
+                need = zj_output_size(&img);
+                rc = zj_validate_image(&img);
+                if (rc == ZJ_OK && need == 0) rc = ZJ_ERR_INVALID_ARG;
+            }
+            uint8_t *dst = out[i];
+            bool mine = false;
+            if (rc == ZJ_OK) {
+                if (dst) { if (out_len[i] < need) rc = ZJ_ERR_SHORT_OUTPUT; }
+                else { dst = (uint8_t *)malloc(need); mine = true; if (!dst) rc = ZJ_ERR_OOM; }
+            }
+            if (rc == ZJ_OK) rc = zj_gpu_reconstruct(opt.device, nullptr, &img, 1, &dst, &need);
+            if (rc == ZJ_OK) { out[i] = dst; out_len[i] = need; }
+            else { if (mine) free(dst); if (mine || !out[i]) out[i] = nullptr; out_len[i] = 0; failed++; }
+            status[i] = rc;
+        }
+        if (d) {
+            std::lock_guard<std::mutex> lock(idle_mu);
+            if (idle.size() < 256) { idle.push_back(d); d = nullptr; }
+        }
+        zj_decoder_free(d);
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    if (n) worker();
+    for (auto &t : pool) t.join();
+    return failed.load();
+}
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d) { return d ? d->err_kind : ZJ_DE_NONE; }
 ZJ_API const char *zj_decoder_error(const zj_decoder *d) { return d ? d->err_display.c_str() : ""; }
 

@@ -273,3 +273,45 @@ class Decoder:
 JpegDecoder = Decoder
 DecoderOptions = ZuneJpegOptions
 UnsupportedSchemes = enum.Enum("UnsupportedSchemes", "ExtendedSequentialHuffman LosslessHuffman ExtendedSequentialDctArithmetic ProgressiveDctArithmetic LosslessArithmetic")
+
+
+def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None):
+    """zj_decode_batch: JPEG byte strings in, pixel bytes out, `threads` host threads (0 = one per hardware thread)
+    running the host stage of different images side by side while the GPU reconstructs the finished ones.
+
+    Returns a list with one entry per input: `bytes` (or, with `out`, the number of bytes written into out[i]) for a decoded
+    image, a `DecodeErrors` instance for a failed one.  `out`: optional list of writable buffers (e.g. PinnedBuffer.array
+    slices), one per image, large enough for width*height*components."""
+    import numpy as np
+    lib = _ffi.load()
+    options = options if options is not None else ZuneJpegOptions()
+    raw = options._raw()
+    raw.num_threads = int(threads)
+    n = len(buffers)
+    keep = [bytes(b) for b in buffers]
+    bufs = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p).value for b in keep])
+    lens = (C.c_size_t * n)(*[len(b) for b in keep])
+    outs = (C.c_void_p * n)()
+    out_len = (C.c_size_t * n)()
+    status = (C.c_int * n)()
+    if out is not None:
+        views = [np.frombuffer(o, dtype=np.uint8) if not isinstance(o, np.ndarray) else o for o in out]
+        for i, v in enumerate(views):
+            outs[i] = v.ctypes.data
+            out_len[i] = v.nbytes
+    rc = lib.zj_decode_batch(C.byref(raw), bufs, lens, n, outs, out_len, status)
+    if rc < 0:
+        raise DecodeErrors(13, lib.zj_gpu_strerror(rc).decode(), rc)
+    res = []
+    for i in range(n):
+        if status[i] != 0:
+            res.append(DecodeErrors(13 if status[i] != _ffi.ERR_DECODE else 1, lib.zj_gpu_strerror(status[i]).decode(), status[i]))
+        elif out is not None:
+            res.append(int(out_len[i]))
+        else:
+            try:
+                res.append(C.string_at(outs[i], out_len[i]))
+            finally:
+                lib.zj_buffer_free(outs[i])
+    return res
+
