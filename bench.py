@@ -78,14 +78,54 @@ def make_pool(cfg: str, n_distinct: int, rank: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The region of the default run
+    is only tens of milliseconds long, so the clocks are polled through NVML from a thread (every ~2 ms); nvidia-smi -lms is
+    the fallback when the NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.device, self.proc, self.path = device, None, None
+        self.thread, self.stop_flag, self.samples, self.h, self.nv = None, False, [], None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            import torch
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES through the PCI bus id of the CUDA device
+            bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(torch.cuda.get_device_properties(device), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+                        break
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            import threading
+            self.stop_flag, self.samples = False, []
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
@@ -96,6 +136,26 @@ class ClockSampler:
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            if self.samples:
+                sm = [x[0] for x in self.samples]
+                out["sm_mhz"] = float(statistics.median(sm))
+                try:
+                    out["sm_max_mhz"] = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+                except Exception:
+                    pass
+                out["power_w_max"] = round(max(x[1] for x in self.samples), 2)
+                out["samples"] = len(sm)
+                bits = 0
+                for x in self.samples:
+                    bits |= int(x[2])
+                names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+                out["reasons"] = [n for n, b in names.items() if bits & b]
+                out["how"] = "NVML polled every ~2 ms during the timed region"
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
