@@ -286,3 +286,13 @@ def test_decode_batch_matches_single_image_decodes():
     assert res == sizes
     for j, o in zip(jpegs, outs):
         assert o.tobytes() == Decoder.new_with_options(opts).decode_buffer(j)
+
+
+@pytest.mark.parametrize("w,h,mode", [(2500, 1786, "444"), (2500, 1786, "422"), (2500, 1786, "440"), (3024, 4032, "420"),
+                                      (1920, 1080, "422"), (7680, 4320, "444"), (7680, 4320, "422"), (7680, 4320, "440")])
+def test_reference_fixture_geometries(w, h, mode):
+    """The shapes of the reference's own integration fixtures (tests/inputs/medium_*_2500x1786, google_pixel 3024x4032 2x2,
+    single_qt 1920x1080 2x1, large_*_7680_4320) with random coefficient planes: the reference only eyeballs
+    these outputs, here they must equal the oracle byte for byte."""
+    rng = np.random.default_rng(hash((w, h, mode)) & 0xFFFF)
+    assert _run_case(rng, w, h, mode, 0, 0) == "ok"
