@@ -1310,9 +1310,16 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         const u32 zslot = ((u32)__cvta_generic_to_shared(sDynAll) + 3u * ZF_PRODUCERS * 128u) | (u32)((lane & 7) * 16);
         if (rtid < 8) sts128(zslot - (u32)((lane & 7) * 16) + (u32)rtid * 16u, 0u, 0u, 0u, 0u);
         asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_QUEUE + 1), "n"(ZF_PRODUCERS) : "memory");   // producers only
+        // (these four are a few integer operations each from the lane index; made opaque so that they are kept instead of
+        // being recomputed in every pass)
+        asm volatile("" : "+r"(const_cast<u32 &>(d_even)), "+r"(const_cast<u32 &>(d_odd)), "+r"(const_cast<u32 &>(slx)), "+r"(const_cast<u32 &>(scr)));
         auto issue = [&](const int ps, const int16_t *g0, const int16_t *g1, const u32 m) {
             const u32 off = 0u;
-            if (m & 0x100u) {
+            if (ZF_LIKELY(m == 0xffu)) {   // a full job: no per-chunk predicates
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(((k & 1) ? d_odd : d_even) + off + k * 512u), "l"((k < 4 ? g0 : g1) + k * 256) : "memory");
+            } else if (m & 0x100u) {
 #pragma unroll
                 for (int r = 0; r < 8; r++)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((slx + off) ^ (u32)(r << 4)), "l"(g0 + r * 8) : "memory");
