@@ -355,27 +355,54 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
                                             AfterRows after_rows)
 {
     constexpr u32 CH = 16u * ZF_PRODUCERS;
-    u32 acc = 0, acc47 = 0, acc67 = 0, dcmask = 0xffff0000u, dc0 = 0;
+    u32 acc = 0, dcmask = 0xffff0000u, dc0 = 0;
+    bool rows45 = false, rows67 = false;       // warp-uniform: anything in rows 4-5 / 6-7 of any block of the warp
 #pragma unroll 1
     for (int rp = 0; rp < 4; rp++) {          // rows 2rp, 2rp+1
         u32 a0, a1, a2, a3, b0, b1, b2, b3;
         const u32 pa = sl ^ (u32)(rp << 5);
         lds128(pa, a0, a1, a2, a3);
         lds128(pa ^ 16u, b0, b1, b2, b3);
-        const uint4 qa = *reinterpret_cast<const uint4 *>(qtw + rp * 8), qb = *reinterpret_cast<const uint4 *>(qtw + rp * 8 + 4);
         if (rp == 0) dc0 = a0;
         const u32 hi = a2 | a3 | b2 | b3, all = a0 | a1 | b0 | b1 | hi;
         acc |= (a0 & dcmask) | a1 | b0 | b1 | hi;
         dcmask = 0xffffffffu;
-        if (rp >= 2) acc47 |= all;
-        if (rp == 3) acc67 = all;
-        // the pair is skipped when it is zero in every block of the warp, and uses the 4-input form when nothing sits in columns 4-7
-        const bool any = __any_sync(0xffffffffu, all != 0), anyhi = __any_sync(0xffffffffu, hi != 0);
         const u32 o = sc + (u32)(rp * 4) * CH;
-        row_pass(any, anyhi, a0, a1, a2, a3, qa, o);
-        row_pass(any, anyhi, b0, b1, b2, b3, qb, o + 2 * CH);
+        // the pair is skipped when it is zero in every block of the warp (a zero row transforms to exact zeros) ...
+        if (!__any_sync(0xffffffffu, all != 0)) {
+            if (rp < 2) {                      // (rows 4-7: zeroed below, and only if the column pass will read them)
+#pragma unroll
+                for (int k = 0; k < 4; k++) sts128(o + (u32)k * CH, 0u, 0u, 0u, 0u);
+            }
+            continue;
+        }
+        if (rp == 2) rows45 = true;
+        if (rp == 3) rows67 = true;
+        // ... and uses the 4-input form when nothing sits in columns 4-7
+        const bool anyhi = __any_sync(0xffffffffu, hi != 0);
+        const uint4 qa = *reinterpret_cast<const uint4 *>(qtw + rp * 8), qb = *reinterpret_cast<const uint4 *>(qtw + rp * 8 + 4);
+        u32 s0 = dp2a_lo(a0, qa.x), s1 = dp2a_hi(a0, qa.x), s2 = dp2a_lo(a1, qa.y), s3 = dp2a_hi(a1, qa.y), s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+        u32 t0 = dp2a_lo(b0, qb.x), t1 = dp2a_hi(b0, qb.x), t2 = dp2a_lo(b1, qb.y), t3 = dp2a_hi(b1, qb.y), t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+        if (anyhi) {
+            s4 = dp2a_lo(a2, qa.z); s5 = dp2a_hi(a2, qa.z); s6 = dp2a_lo(a3, qa.w); s7 = dp2a_hi(a3, qa.w);
+            t4 = dp2a_lo(b2, qb.z); t5 = dp2a_hi(b2, qb.z); t6 = dp2a_lo(b3, qb.w); t7 = dp2a_hi(b3, qb.w);
+            idct8<10>(s0, s1, s2, s3, s4, s5, s6, s7, 512u);
+            idct8<10>(t0, t1, t2, t3, t4, t5, t6, t7, 512u);
+        } else {
+            idct8_lo4<10>(s0, s1, s2, s3, s4, s5, s6, s7, 512u);
+            idct8_lo4<10>(t0, t1, t2, t3, t4, t5, t6, t7, 512u);
+        }
+        sts128(o, s0, s1, s2, s3);
+        sts128(o + CH, s4, s5, s6, s7);
+        sts128(o + 2 * CH, t0, t1, t2, t3);
+        sts128(o + 3 * CH, t4, t5, t6, t7);
     }
-    const bool rows47 = __any_sync(0xffffffffu, acc47 != 0), rows67 = __any_sync(0xffffffffu, acc67 != 0);
+    const bool rows47 = rows45 || rows67;
+    if (rows47 && !(rows45 && rows67)) {       // the 8-input column pass reads rows 4-7: zero the pair that was skipped
+        const u32 o = sc + (u32)(rows45 ? 12 : 8) * CH;
+#pragma unroll
+        for (int k = 0; k < 4; k++) sts128(o + (u32)k * CH, 0u, 0u, 0u, 0u);
+    }
     __syncwarp();
     after_rows();                             // every lane of the warp is done with its staging slot
     // all 63 AC coefficients zero: ((c0 as i16).wrapping_mul(q0 as i16) >> 3) + 128 in i16, clamped (avx2.rs:159-167) --
@@ -388,9 +415,6 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
     if (!rows47) {                            // rows 4-7 are zero in every block of the warp
 #pragma unroll 1
         for (int g = 0; g < 2; g++) col_pass<4>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
-    } else if (ZF_LO6 && !rows67) {           // rows 6-7 are zero in every block of the warp
-#pragma unroll 1
-        for (int g = 0; g < 2; g++) col_pass<6>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
     } else {
 #pragma unroll 1
         for (int g = 0; g < 2; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
