@@ -38,11 +38,11 @@ constexpr int TM_NONE = 40 * ZJ_THREADS / 128, TM_H = 15 * ZJ_THREADS / 128, TM_
 #define ZF_CFG_MINBLOCKS 3
 #endif
 #ifndef ZF_CFG_SPC
-#define ZF_CFG_SPC 16
+#define ZF_CFG_SPC 40
 #endif
 constexpr int ZF_THREADS = 256, ZF_PRODUCERS = 128, ZF_CONSUMERS = 128;
 constexpr int ZF_MINBLOCKS = ZF_CFG_MINBLOCKS;
-constexpr int ZF_DEFAULT_SPC = ZF_CFG_SPC;      // strips per CTA
+constexpr int ZF_DEFAULT_SPC = ZF_CFG_SPC;      // target strips per CTA (see strips_per_cta)
 // unit columns (16 luma samples) per tile: 2 * ZF_CONSUMERS / row groups per strip
 constexpr int ZF_XU_GRAY = 32;                  // luma-only fast kernel: 512-sample tiles
 constexpr int ZF_XU_NONE = 2 * ZF_CONSUMERS / 8, ZF_XU_H = 2 * ZF_CONSUMERS / 16, ZF_XU_V = 2 * ZF_CONSUMERS / 8, ZF_XU_HV = 2 * ZF_CONSUMERS / 16;

@@ -1804,17 +1804,35 @@ gray_fast_kernel(const DevImage *__restrict__ images, const int spc)
     }
 }
 
-static int g_spc = 0;  // strips per CTA of the fast kernel (0 = default; ZJ_SPC in the environment overrides)
+// Strips per CTA of the fast kernels.  A CTA pays one pipeline fill / drain per strip range, so ranges should be long
+// (about ZF_DEFAULT_SPC strips, equal parts of the image); but the launch must still offer a few CTAs per resident slot
+// (3 per SM), so small batches are cut finer.  ZJ_SPC in the environment overrides.
+static int strips_per_cta(const LaunchGroup &g)
+{
+    static int forced = -1, slots = 0;
+    if (forced < 0) {
+        const char *e = getenv("ZJ_SPC");
+        forced = e ? (atoi(e) < 1 ? 1 : atoi(e)) : 0;
+    }
+    if (forced) return forced;
+    if (slots == 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        slots = 3 * sms;
+    }
+    const long S = g.max_strips > 0 ? (long)g.max_strips : 1;
+    long parts = (S + ZF_DEFAULT_SPC - 1) / ZF_DEFAULT_SPC;
+    const long columns = (long)g.max_tiles * (long)g.count;
+    while (columns * parts < 2L * slots && S / parts > 4) parts++;
+    return (int)((S + parts - 1) / parts);
+}
 
 template <int MODE>
 static cudaError_t launch_fast(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
 {
-    if (g_spc == 0) {
-        const char *e = getenv("ZJ_SPC");
-        g_spc = e ? atoi(e) : ZF_DEFAULT_SPC;
-        if (g_spc < 1) g_spc = 1;
-    }
-    dim3 grid(g.max_tiles, (g.max_strips + g_spc - 1) / g_spc + 1, g.count);
+    const int spc = strips_per_cta(g);
+    dim3 grid(g.max_tiles, (g.max_strips + spc - 1) / spc + 1, g.count);
     typedef FastTraits<MODE> FT;
     constexpr int NB = (MODE == MODE_V || MODE == MODE_NONE) ? 2 : ZF_NBUF;
     constexpr size_t smem = 3 * ZF_PRODUCERS * 128 + 128 + (size_t)NB * FT::BUF + ZF_EXPERIMENT_PAD;
@@ -1826,18 +1844,14 @@ static cudaError_t launch_fast(const DevImage *d_images, const LaunchGroup &g, c
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    reconstruct_fast_kernel<MODE><<<grid, ZF_THREADS, smem, stream>>>(d_images + g.first, g_spc);
+    reconstruct_fast_kernel<MODE><<<grid, ZF_THREADS, smem, stream>>>(d_images + g.first, spc);
     return cudaGetLastError();
 }
 
 static cudaError_t launch_gray_fast(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream)
 {
-    if (g_spc == 0) {
-        const char *e = getenv("ZJ_SPC");
-        g_spc = e ? atoi(e) : ZF_DEFAULT_SPC;
-        if (g_spc < 1) g_spc = 1;
-    }
-    dim3 grid(g.max_tiles, (g.max_strips + g_spc - 1) / g_spc + 1, g.count);   // max_strips: pairs of block rows
+    const int spc = strips_per_cta(g);
+    dim3 grid(g.max_tiles, (g.max_strips + spc - 1) / spc + 1, g.count);   // max_strips: pairs of block rows
     constexpr size_t smem = 3 * ZF_PRODUCERS * 128 + 128 + 2 * ZG_BUF;
     static bool configured[64] = {false};
     int dev = 0;
@@ -1847,7 +1861,7 @@ static cudaError_t launch_gray_fast(const DevImage *d_images, const LaunchGroup 
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    gray_fast_kernel<<<grid, ZF_THREADS, smem, stream>>>(d_images + g.first, g_spc);
+    gray_fast_kernel<<<grid, ZF_THREADS, smem, stream>>>(d_images + g.first, spc);
     return cudaGetLastError();
 }
 
