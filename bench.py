@@ -87,6 +87,7 @@ class ClockSampler:
     def __init__(self, device: int):
         self.device, self.proc, self.path = device, None, None
         self.thread, self.stop_flag, self.samples, self.h, self.nv = None, False, [], None, None
+        self.t_mark = 0.0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -108,16 +109,20 @@ class ClockSampler:
         nv, h = self.nv, self.h
         while not self.stop_flag:
             try:
+                t = time.perf_counter()
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
                 try:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, pw, rs))
+                self.samples.append((sm, t, rs))
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.001)
+
+    def mark(self):
+        """start of the timed region (the thread is started before the warm-up steps so that it is up to speed)"""
+        self.t_mark = time.perf_counter()
 
     def start(self):
         if self.nv is not None:
@@ -140,21 +145,25 @@ class ClockSampler:
             self.stop_flag = True
             self.thread.join(timeout=2)
             nv = self.nv
-            if self.samples:
-                sm = [x[0] for x in self.samples]
+            inside = [x for x in self.samples if x[1] >= getattr(self, "t_mark", 0.0)]
+            how = "NVML polled every ~1 ms during the timed region"
+            if len(inside) < 3:   # a slow NVML call can straddle a region of a few tens of ms: fall back to the warm-up steps too
+                inside, how = self.samples, "NVML polled every ~1 ms during the warm-up and timed steps (same workload)"
+            if inside:
+                sm = [x[0] for x in inside]
                 out["sm_mhz"] = float(statistics.median(sm))
                 try:
                     out["sm_max_mhz"] = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    out["power_w_end"] = round(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, 2)
                 except Exception:
                     pass
-                out["power_w_max"] = round(max(x[1] for x in self.samples), 2)
                 out["samples"] = len(sm)
                 bits = 0
-                for x in self.samples:
+                for x in inside:
                     bits |= int(x[2])
                 names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
                 out["reasons"] = [n for n, b in names.items() if bits & b]
-                out["how"] = "NVML polled every ~2 ms during the timed region"
+                out["how"] = how
             return out
         if self.proc is None:
             return out
@@ -305,12 +314,13 @@ def run_ours(args):
             raise SystemExit("bench.py: GPU output differs from the oracle -- refusing to report a number")
 
     # ---- timed region: W warm-up steps, then exactly K steps between barriers, CUDA events on the launching stream
+    sampler = ClockSampler(device)
+    sampler.start()
     for _ in range(args.warmup):
         plan.run(stream.ptr)
     stream.synchronize()
     pl.barrier()
-    sampler = ClockSampler(device)
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = gpu.Event(device), gpu.Event(device)
     launches0 = gpu.launch_count()
     ev0.record(stream.ptr)
