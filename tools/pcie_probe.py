@@ -1,0 +1,31 @@
+"""tools/pcie_probe.py -- what the host link gives (run on the GPU box): pinned H2D, D2H, and both at once."""
+import time
+import torch
+
+n = 1 << 30
+h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+
+def run(h2d, d2h, reps=5):
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(reps):
+        if h2d:
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+        if d2h:
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    return reps * n / dt / 1e9
+
+
+run(True, True, 1)
+print("H2D alone   %.1f GB/s" % run(True, False))
+print("D2H alone   %.1f GB/s" % run(False, True))
+print("both at once %.1f GB/s each" % run(True, True))

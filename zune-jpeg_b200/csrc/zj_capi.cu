@@ -405,7 +405,14 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
     cudaStream_t st[NS_MAX];
     // the staging streams are created once per host thread and device and reused: creating / destroying streams takes
     // driver-wide locks, which hurts when many threads call in (zj_decode_batch)
-    struct StreamCache { cudaStream_t s[64][NS_MAX] = {}; };
+    // ... and so is the device staging buffer of every stream (grown on demand, reused in stream order): memory that the
+    // stream-ordered pool hands from one stream to another makes the second stream wait for the first one's work, which
+    // serialises the upload of one sub-batch behind the download of the previous one
+    struct StreamCache {
+        cudaStream_t s[64][NS_MAX] = {};
+        uint8_t *buf[64][NS_MAX] = {};
+        size_t cap[64][NS_MAX] = {};
+    };
     thread_local StreamCache cache;
     if (device >= 64) return ZJ_ERR_NO_DEVICE;
     for (int k = 0; k < NS; k++) {
@@ -435,10 +442,15 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
         }
         cudaStream_t s = st[which];
         which = (which + 1) % NS;
-        uint8_t *pool = nullptr;
-        cudaError_t e = cudaMallocAsync((void **)&pool, bytes, s);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocAsync"); break; }
-        to_free.push_back(pool);
+        const int slot = (which + NS - 1) % NS;          // index of stream s
+        cudaError_t e = cudaSuccess;
+        if (cache.cap[device][slot] < bytes) {
+            if (cache.buf[device][slot]) { cudaStreamSynchronize(s); cudaFree(cache.buf[device][slot]); cache.buf[device][slot] = nullptr; cache.cap[device][slot] = 0; }
+            e = cudaMalloc((void **)&cache.buf[device][slot], bytes + bytes / 8);
+            if (e != cudaSuccess) { cache.buf[device][slot] = nullptr; rc = cuda_fail(e, "cudaMalloc(staging)"); break; }
+            cache.cap[device][slot] = bytes + bytes / 8;
+        }
+        uint8_t *pool = cache.buf[device][slot];
         std::vector<zj_image> dimgs(imgs + i, imgs + j);
         std::vector<uint8_t *> douts(j - i);
         std::vector<size_t> dlens(j - i);
@@ -466,8 +478,6 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
             e = cudaMemcpyAsync(out[k], douts[k - i], plans[k].out_size, cudaMemcpyDeviceToHost, s);
             if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
         }
-        cudaFreeAsync(pool, s);
-        to_free.pop_back();
         i = j;
     }
     for (int k = 0; k < NS; k++) {
