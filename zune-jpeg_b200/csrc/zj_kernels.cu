@@ -1243,6 +1243,11 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const int warp = tid >> 5;
     const bool producer = (warp & 2) == 0;
     const int rtid = ((warp >> 2) * 64) + ((warp & 1) * 32) + (tid & 31);   // thread index inside the role
+#elif ZF_ROLEMAP == 2
+    // producers in the UPPER warps of the CTA: the warp scheduler favours higher warp slots, and the producers are the
+    // critical path of the pipeline
+    const bool producer = tid >= ZF_CONSUMERS;
+    const int rtid = producer ? tid - ZF_CONSUMERS : tid;
 #else
     const bool producer = tid < ZF_PRODUCERS;
     const int rtid = producer ? tid : tid - ZF_PRODUCERS;
