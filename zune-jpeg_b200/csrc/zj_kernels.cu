@@ -48,6 +48,17 @@
 #define ZF_EMIT_LOOP 0
 #endif
 
+// The per-sample generic path (slow_pixel) used to be kept out of line.  With that call inside a consumer warp,
+// compute-sanitizer's synccheck reported divergent threads at the next named barrier (results and racecheck were clean);
+// inlined -- only its leaf ChromaView::at stays a call -- memcheck, racecheck and synccheck are all clean and the headline
+// config is no slower (tools/sanitize_cases.py).
+#ifndef ZJ_NOINLINE
+#define ZJ_NOINLINE __forceinline__
+#endif
+#ifndef ZJ_NOINLINE_AT
+#define ZJ_NOINLINE_AT __noinline__   // ChromaView::at, the leaf every generic sample fetch goes through, stays a call (code size)
+#endif
+
 namespace zj {
 
 typedef uint32_t u32;
@@ -440,7 +451,7 @@ struct ChromaView {
     int lhb, rhb, spb;  // block columns held in the left / right / special halo slots (-1 = none)
     int cs;          // smem row stride (samples)
     unsigned long long magic_w;  // ceil(2^40 / W)
-    __device__ __noinline__ int at(int row, int col) const
+    __device__ ZJ_NOINLINE_AT int at(int row, int col) const
     {
         int lc;
         if (col >= c0 && col < c1) lc = 8 + (col - c0);
@@ -588,7 +599,7 @@ __device__ __forceinline__ void ycc_to_rgb(int y, int cb, int cr, u32 &r, u32 &g
 
 
 // ------------------------------------------------------------------------- generic (edge) path, out of line
-// Every quirk of the reference, any variant, one sample at a time.  Kept __noinline__ so that the hot loop of
+// Every quirk of the reference, any variant, one sample at a time.  (ZJ_NOINLINE: see the top of the file; the hot loop of
 // the kernel stays small enough for the instruction cache; only edge units of a tile come here.
 template <typename ST>
 struct SlowCtx {
@@ -601,7 +612,7 @@ struct SlowCtx {
 };
 
 template <int MODE, int VARIANT, typename ST>
-__device__ __noinline__ void slow_pixel(const SlowCtx<ST> &c, int yl, int x)  // x = tile-local luma column
+__device__ ZJ_NOINLINE void slow_pixel(const SlowCtx<ST> &c, int yl, int x)  // x = tile-local luma column
 {
     const u32 y = c.y_base + yl;
     if (y >= c.height) return;                 // rows past the image are truncated (mcu.rs:375)
@@ -630,7 +641,7 @@ __device__ __noinline__ void slow_pixel(const SlowCtx<ST> &c, int yl, int x)  //
 // width < 16: the first 16 samples (zero-padded past Wp) are converted into a 16*nc-byte temp and its first
 // width*nc bytes are copied out (worker.rs:176-198).  A single tile covers the row.
 template <int MODE, int VARIANT, typename ST>
-__device__ __noinline__ void slow_small_width(const SlowCtx<ST> &c, int rows, int tid)
+__device__ ZJ_NOINLINE void slow_small_width(const SlowCtx<ST> &c, int rows, int tid)
 {
     const u32 rowbytes = c.width * c.nc;
     for (int u = tid; u < rows * 16; u += ZJ_THREADS) {
@@ -1104,9 +1115,11 @@ __device__ __forceinline__ u32 evens(u32 w) { return prmt(w, 0u, 0x4240u); }  //
 __device__ __forceinline__ u32 odds(u32 w) { return prmt(w, 0u, 0x4341u); }   // bytes 1,3 -> 16-bit lanes
 
 // named barriers (id 0 is __syncthreads); count = every thread of the CTA: one half arrives, the other half waits
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ZF_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_sync_consumers(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ZF_CONSUMERS) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ZF_THREADS) : "memory"); }
+// (bar.sync / bar.arrive are warp-aligned instructions: the warp is re-converged first -- the generic per-sample path and
+// the zero-fill loops leave lanes of a consumer warp at different places)
+__device__ __forceinline__ void bar_sync(int id) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ZF_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_sync_consumers(int id) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ZF_CONSUMERS) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ZF_THREADS) : "memory"); }
 
 // Horizontal x2 triangle filter of eight samples R0..R7 (r[k] = (R2k, R2k+1) as lane pairs) with outer neighbours
 // h = (R(-1), R8):  out[2i] = T(R[i], R[i-1]), out[2i+1] = T(R[i], R[i+1])  (upsampler/scalar.rs:30-42 == avx2.rs:178-197)
@@ -1457,6 +1470,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const u32 zper = ((zlen / zg + nt - 1) / nt) * zg;             // bytes per tile (multiple of the store size)
     const u32 zb0 = min(z0 + tile * zper, stride), zb1 = min(zb0 + zper, stride);
     const int zcnt = (int)((zb1 - zb0) / zg);                     // stores per row for this tile
+    const int zrpp = (zcnt > 0 && zcnt < ZF_CONSUMERS) ? ZF_CONSUMERS / zcnt : 1;           // rows covered per pass of the consumer threads
+    const int zr0 = (zcnt > 0 && zcnt < ZF_CONSUMERS) ? (tc / zcnt < zrpp ? tc / zcnt : ROWS) : 0;
+    const int zk0 = (zcnt > 0 && zcnt < ZF_CONSUMERS) ? tc % zcnt : tc;
 
     int buf = 0;
     for (int it = 0; it < n_it; it++) {
@@ -1603,31 +1619,44 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             sc.stride = stride; sc.n_norm = n_norm; sc.T = T; sc.ycc = ycc; sc.out = out; sc.width = im.width; sc.nc = im.nc;
             if (nslow > ZJ_SLOW_CAP) {
                 const int tw = nyb * 8;
-                for (int u = tc; u < ROWS * tw; u += ZF_CONSUMERS) { const int yl = u / tw; slow_pixel<MODE, 0, ST>(sc, yl, u - yl * tw); }
+                // (every lane makes the same number of trips, so the warps arrive at the barriers below in one piece)
+                for (int u0s = 0; u0s < ROWS * tw; u0s += ZF_CONSUMERS) {
+                    const int u = u0s + tc;
+                    if (u < ROWS * tw) { const int yl = u / tw; slow_pixel<MODE, 0, ST>(sc, yl, u - yl * tw); }
+                }
             } else {
-                for (int t = tc; t < nslow * 16 * RPU; t += ZF_CONSUMERS) {
-                    const int e = sSlow[t / (16 * RPU)], r = (t >> 4) % RPU, k = t & 15;
-                    const int g = e >> 8, xl2 = (e & 0xff) << 3;
-                    int yl;
-                    if (MODE == MODE_V) yl = 2 * g + r;
-                    else if (MODE == MODE_HV) yl = 4 * (g >> 1) + (g & 1) + 2 * r;
-                    else yl = g;
-                    if (xl2 + k < nyb * 8) slow_pixel<MODE, 0, ST>(sc, yl, xl2 + k);
+                const int total = nslow * 16 * RPU;
+                for (int t0s = 0; t0s < total; t0s += ZF_CONSUMERS) {
+                    const int t = t0s + tc;
+                    if (t < total) {
+                        const int e = sSlow[t / (16 * RPU)], r = (t >> 4) % RPU, k = t & 15;
+                        const int g = e >> 8, xl2 = (e & 0xff) << 3;
+                        int yl;
+                        if (MODE == MODE_V) yl = 2 * g + r;
+                        else if (MODE == MODE_HV) yl = 4 * (g >> 1) + (g & 1) + 2 * r;
+                        else yl = g;
+                        if (xl2 + k < nyb * 8) slow_pixel<MODE, 0, ST>(sc, yl, xl2 + k);
+                    }
                 }
             }
+            __syncwarp();
         }
         if (it + NB < n_it) bar_arrive(BAR_EMPTY + buf);          // the producers may refill this buffer
         buf = buf + 1 == NB ? 0 : buf + 1;
         if (ZF_UNLIKELY(zcnt > 0)) {
-            for (int u = tc; u < ROWS * zcnt; u += ZF_CONSUMERS) {
-                const int yl = u / zcnt, k = u - yl * zcnt;
-                const u32 y = y_base + yl;
+            // thread -> (row zr0 + i * zrpp, store zk0 + j * ZF_CONSUMERS): no divisions inside the strip loop
+            for (int yl = zr0; yl < ROWS; yl += zrpp) {
+                const u32 y = y_base + (u32)yl;
                 if (y >= im.height) break;
-                uint8_t *z = out + (size_t)y * stride + zb0 + (size_t)k * zg;
-                if (zg == 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0u, 0u, 0u, 0u);
-                else if (zg == 4) *reinterpret_cast<u32 *>(z) = 0u;
-                else *z = 0;
+                uint8_t *zrow = out + (size_t)y * stride + zb0;
+                for (int k = zk0; k < zcnt; k += ZF_CONSUMERS) {
+                    uint8_t *z = zrow + (size_t)k * zg;
+                    if (zg == 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0u, 0u, 0u, 0u);
+                    else if (zg == 4) *reinterpret_cast<u32 *>(z) = 0u;
+                    else *z = 0;
+                }
             }
+            __syncwarp();
         }
     }
 }
