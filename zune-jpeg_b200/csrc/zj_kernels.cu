@@ -1392,9 +1392,11 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
                 if (ps == 0 && it >= NB) bar_sync(BAR_EMPTY + buf);   // the consumers are done with this buffer
+                // the copy issued from this pass: the warp's pass-1 job of this strip, or its pass-0 job of the next strip
+                // (one call site: the copy code exists once in the loop)
                 auto refill = [&]() {
-                    if (ps == 0) { issue(1, qa1, qb1, jm1); qa1 += st1; qb1 += st1; }
-                    else if (it + 1 < n_it) { issue(0, qa0, qb0, jm0); qa0 += st0; qb0 += st0; }
+                    issue(ps, ps ? qa0 : qa1, ps ? qb0 : qb1, ps ? (it + 1 < n_it ? jm0 : 0u) : jm1);
+                    if (ps) { qa0 += st0; qb0 += st0; } else { qa1 += st1; qb1 += st1; }
                 };
                 if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
                 else refill();
