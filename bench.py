@@ -449,6 +449,34 @@ def run_ours(args):
             decode["cpu"] = {"value": round(nc * w * h / 1e6 / dtc, 2), "unit": "MP/s", "threads": threads, "images": nc,
                              "how": "the same host stage + the oracle port of the pixel path, one image per thread"}
 
+    # ---- one image at a time: when the JPEG carries restart markers its intervals are entropy-decoded side
+    # by side on the host threads; latency of Decoder.decode_buffer-style calls with 1 thread (the reference's loop) and all
+    if decode is not None and b"\xff\xdd" in jpegs[0][:4096]:
+        from zune_jpeg_b200 import _ffi
+        lib = _ffi.load()
+        single = {}
+        one_out = pinned_dec.ptr
+        for label, nt in (("sequential", 1), ("parallel", threads)):
+            d1 = Decoder.new_with_options(opts.set_num_threads(nt))
+            img1 = ZjImage()
+            best_h, best_t, seg = 1e9, 1e9, 0
+            for _ in range(4):
+                t0 = time.perf_counter()
+                rc = lib.zj_decoder_decode_coefficients(d1._h, jpegs[0], len(jpegs[0]), C.byref(img1))
+                t1 = time.perf_counter()
+                if rc == 0:
+                    o1, l1 = (C.c_void_p * 1)(one_out), (C.c_size_t * 1)(out_bytes)
+                    rc = lib.zj_gpu_reconstruct(device, None, C.byref(img1), 1, o1, l1)
+                t2 = time.perf_counter()
+                if rc != 0:
+                    raise SystemExit(f"bench.py: single-image decode failed: {rc}")
+                best_h, best_t, seg = min(best_h, t1 - t0), min(best_t, t2 - t0), d1.entropy_segments()
+            if not args.no_check and not np.array_equal(pinned_dec.array[:out_bytes], want):
+                raise SystemExit("bench.py: single-image decode differs from the oracle")
+            single[label] = {"threads": nt, "intervals_side_by_side": int(seg), "host_stage_ms": round(best_h * 1e3, 2),
+                             "total_ms": round(best_t * 1e3, 2), "MP/s": round(w * h / 1e6 / best_t, 1)}
+        decode["single_image"] = single
+
     # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
     peaks = {}
     try:

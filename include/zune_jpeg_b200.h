@@ -214,6 +214,11 @@ ZJ_API uint32_t zj_decoder_out_colorspace(const zj_decoder *d);        /* Decode
 /* Host stage only: headers + entropy decode into coefficient planes owned by the decoder (pinned when a
  * device is present).  `img` is filled with a descriptor pointing at them (valid until the next call). */
 ZJ_API int zj_decoder_decode_coefficients(zj_decoder *d, const uint8_t *buf, size_t len, zj_image *img);
+/* Baseline scans with restart markers (DRI) are entropy-decoded by up to `num_threads` host threads, one restart interval
+ * per thread at a time (src/mcu.rs:253-351 and 386-418 run per interval); the result is kept only when every interval ended
+ * exactly where the next one starts, otherwise the scan is redone by the reference's sequential loop, so the planes are
+ * always what that loop produces.  Returns how many intervals the last decode ran side by side (0 = sequential loop). */
+ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d);
 /* Decoder::decode_buffer: host stage, then zj_gpu_reconstruct.  *out is malloc'd (zj_buffer_free). */
 ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out,
                                     size_t *out_len);

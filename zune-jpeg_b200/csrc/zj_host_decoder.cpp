@@ -493,7 +493,7 @@ struct PlaneBuf {
         if (pinned) cudaFreeHost(p); else free(p);
         p = nullptr; cap = 0;
     }
-    int16_t *ensure_zeroed(size_t n, bool want_pinned)
+    int16_t *ensure_zeroed(size_t n, bool want_pinned, bool zero = true)
     {
         if (n > cap) {
             release();
@@ -503,7 +503,7 @@ struct PlaneBuf {
             if (!p) FAIL(ZJ_DE_FORMAT, "out of memory for coefficient planes");
             cap = want;
         }
-        memset(p, 0, n * 2);
+        if (zero) memset(p, 0, n * 2);
         return p;
     }
 };
@@ -532,6 +532,9 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
     PlaneBuf planes[3];
     size_t plane_len[3] = {0, 0, 0};
     bool have_device = false;
+    // restart-interval-parallel entropy decode: threads to use (0 = options.num_threads) and how many intervals the last
+    // decode ran side by side (0 = the sequential loop)
+    size_t entropy_threads = 0, last_entropy_segments = 0;
 
     explicit zj_decoder(const zj_options &o) : options(o)
     {
@@ -832,6 +835,157 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
     }
 
     // ---------------------------------------------------------------- baseline entropy stage (mcu.rs:127-351)
+    // State the MCU loop of mcu.rs:253-351 carries from block to block.  The sequential decode owns one for the whole
+    // scan; the restart-interval-parallel decode gives every interval its own.
+    struct ScanState {
+        BitStream stream;
+        int32_t dc_pred[3] = {0, 0, 0};
+        size_t todo = 0;
+    };
+    struct BaselineGeom {
+        size_t mcu_w = 0, mcu_h = 0, bias = 1, width_stride = 0, hv_width_stride = 0, out_nc = 0, ncomp = 0;
+        bool is_hv = false;
+        size_t strip_len[3] = {0, 0, 0};
+    };
+    struct SegmentAbnormal {};   // the interval did not end the way a conformant one does: redo the scan sequentially
+
+    // The MCU loop over MCUs [first, last) in (strip, v, j) order.
+    //   SEGMENT == false: the reference's loop as written (first = 0, last = all): handle_rst / marker handling of
+    //                     mcu.rs:323-348, 386-418.
+    //   SEGMENT == true : one restart interval decoded on its own.  The same state machine, but it must end with the
+    //                     reset of handle_rst exactly after the last component of MCU last-1 (returns true; `must_reset`
+    //                     says whether that is required) and must not meet anything else the sequential loop would
+    //                     react to (an earlier reset, EOI before the end, another marker): those throw SegmentAbnormal
+    //                     and the caller falls back to the sequential loop, which then reproduces whatever the reference
+    //                     does with such a stream.
+    template <bool SEGMENT>
+    bool baseline_mcus(Cursor &reader, ScanState &st, const BaselineGeom &g, const size_t first, const size_t last, const bool must_reset)
+    {
+        int16_t tmp[64];
+        BitStream &stream = st.stream;
+        const size_t per_strip = g.bias * g.mcu_w;
+        for (size_t m = first; m < last; m++) {
+            const size_t strip = m / per_strip, v = (m - strip * per_strip) / g.mcu_w, j = m - strip * per_strip - v * g.mcu_w;
+            for (size_t pos = 0; pos < g.ncomp; pos++) {
+                const Component &component = components[pos];
+                const HuffmanTable &dc_table = dc_tables[component.dc_huff_table & 3];
+                if (!dc_table.present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No DC table for component %s", comp_debug(component.component_id)));
+                const HuffmanTable &ac_table = ac_tables[component.ac_huff_table & 3];
+                if (!ac_table.present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No AC table for component %s", comp_debug(component.component_id)));
+                for (size_t v_samp = 0; v_samp < component.vertical_sample; v_samp++) {
+                    for (size_t h_samp = 0; h_samp < component.horizontal_sample; h_samp++) {
+                        if (std::min(g.out_nc - 1, pos) == pos) {
+                            // mcu.rs:293-312
+                            const size_t is_y = component.component_id == ID_Y ? 1 : 0;
+                            const size_t y_offset = is_y * v * (g.hv_width_stride + (g.hv_width_stride * (component.vertical_sample - 1)));
+                            const size_t another_stride = (g.width_stride * v_samp * (g.is_hv ? 0 : 1)) + g.hv_width_stride * v_samp * (g.is_hv ? 1 : 0);
+                            const size_t yet_another_stride = (g.is_hv ? 1 : 0) * (g.width_stride >> 2) * v * (component.component_id != ID_Y ? 1 : 0);
+                            const size_t start = (j * 64 * component.horizontal_sample) + (h_samp * 64) + another_stride + y_offset + yet_another_stride;
+                            if (start + 64 > g.strip_len[pos]) FAIL(ZJ_DE_GPU, "the reference decoder panics here (block index out of range, mcu.rs:314)");
+                            stream.decode_mcu_block(reader, dc_table, ac_table, planes[pos].p + strip * g.strip_len[pos] + start, st.dc_pred[pos]);
+                        } else {
+                            stream.decode_mcu_block(reader, dc_table, ac_table, tmp, st.dc_pred[pos]);
+                        }
+                    }
+                }
+                st.todo = st.todo - 1;  // wrapping_sub, once per COMPONENT (Q8)
+                if (st.todo == 0) {     // handle_rst, mcu.rs:386-418
+                    st.todo = restart_interval;
+                    if (stream.has_marker) {
+                        if (stream.marker.kind == M_RST) {
+                            stream.reset();
+                            for (int32_t &p : st.dc_pred) p = 0;
+                            if (SEGMENT) {
+                                if (m + 1 == last && pos + 1 == g.ncomp) return true;
+                                throw SegmentAbnormal{};   // a reset in the middle of the interval
+                            }
+                        } else if (stream.marker.kind == M_EOI) {
+                        } else {
+                            FAIL(ZJ_DE_MCU_ERROR, fmt("Marker %s found in bitstream, possibly corrupt jpeg", marker_debug(stream.marker).c_str()));
+                        }
+                    }
+                }
+                if (stream.has_marker) {  // mcu.rs:337-348
+                    if (stream.marker.kind == M_EOI) {
+                        if (SEGMENT && must_reset) throw SegmentAbnormal{};
+                        break;
+                    }
+                    if (stream.marker.kind == M_RST) continue;
+                    if (SEGMENT) throw SegmentAbnormal{};
+                    parse_marker_inner(stream.marker, reader);
+                }
+            }
+        }
+        if (SEGMENT && must_reset) throw SegmentAbnormal{};   // the interval ended without the reader having met its RSTn
+        return false;
+    }
+
+    // Ends of the RSTn markers of the scan that starts at `from` (index of the byte after 0xFF [0xFF..] 0xDn, i.e. where the
+    // bit reader stands after bitstream.rs:200-215 met it).  Stops at the first marker that is not RSTn.
+    static void find_restart_markers(const Cursor &reader, size_t from, size_t want, std::vector<size_t> &ends)
+    {
+        const uint8_t *d = reader.data;
+        const size_t n = reader.len;
+        size_t p = from;
+        while (p < n && ends.size() < want) {
+            const uint8_t *f = (const uint8_t *)memchr(d + p, 0xFF, n - p);
+            if (!f) break;
+            p = (size_t)(f - d) + 1;
+            while (p < n && d[p] == 0xFF) p++;
+            if (p >= n) break;
+            const uint8_t b = d[p++];
+            if (b == 0x00) continue;
+            if (b >= 0xD0 && b <= 0xD7) { ends.push_back(p); continue; }
+            break;
+        }
+    }
+
+    // Restart-interval-parallel form of the loop: with DRI present every interval starts from a known
+    // state (fresh bit reader right after its RSTn, predictors 0, countdown = DRI), so `threads` host threads decode
+    // different intervals side by side, each with the reference's own state machine, straight into the planes.  It is only
+    // kept when EVERY interval ended exactly where the next one was assumed to start (same MCU, same byte); then the
+    // sequential loop would have gone through the very same states.  Anything else returns false with the planes dirty.
+    bool baseline_parallel(const Cursor &reader0, const ScanState &st0, const BaselineGeom &g, size_t threads)
+    {
+        const size_t total = g.mcu_h * g.bias * g.mcu_w;
+        // a conformant stream has DRI MCUs per interval = DRI * ncomp ticks of the countdown (Q8: it ticks once per
+        // component), so it fires ncomp times per interval and only the last firing, at the interval's end, meets the marker
+        const size_t per_seg = restart_interval;
+        if (per_seg == 0 || total <= per_seg) return false;
+        const size_t n_seg = (total + per_seg - 1) / per_seg;
+        std::vector<size_t> ends;
+        ends.reserve(n_seg);
+        find_restart_markers(reader0, reader0.pos, n_seg - 1, ends);
+        if (ends.size() < n_seg - 1) return false;
+        if (threads > n_seg) threads = n_seg;
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= n_seg || bad.load(std::memory_order_relaxed)) return;
+                Cursor rd = reader0;
+                ScanState st;
+                if (k == 0) st = st0;
+                else { rd.pos = ends[k - 1]; st.todo = restart_interval; }
+                const size_t first = k * per_seg, last = std::min(total, first + per_seg);
+                const bool must_reset = k + 1 < n_seg;
+                try {
+                    const bool was_reset = baseline_mcus<true>(rd, st, g, first, last, must_reset);
+                    if (must_reset && (!was_reset || rd.pos != ends[k])) bad = true;
+                } catch (SegmentAbnormal &) { bad = true; }
+                catch (...) { bad = true; }   // a DecodeError: the sequential loop will raise it at the right place
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < threads; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        if (bad) return false;
+        last_entropy_segments = n_seg;
+        return true;
+    }
+
     void decode_baseline(Cursor &reader)
     {
         check_component_dimensions();
@@ -861,65 +1015,65 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             bias = 1;
         }
         const size_t component_capacity = mcu_w * 64;
-        const bool is_hv = sub_sample_ratio == SS_HV;
-        const size_t out_nc = out_components(options.out_colorspace);
-        const size_t width_stride = (component_capacity * components[0].vertical_sample * components[0].horizontal_sample * bias) >> 1;
-        const size_t hv_width_stride = width_stride >> 1;
+        BaselineGeom g;
+        g.mcu_w = mcu_w; g.mcu_h = mcu_h; g.bias = bias;
+        g.is_hv = sub_sample_ratio == SS_HV;
+        g.out_nc = out_components(options.out_colorspace);
+        g.ncomp = in_components();
+        g.width_stride = (component_capacity * components[0].vertical_sample * components[0].horizontal_sample * bias) >> 1;
+        g.hv_width_stride = g.width_stride >> 1;
         // the reference's output Vec must have one chunk per strip, or chunks.next().unwrap() panics (mcu.rs:354)
         {
             const size_t capacity = (size_t)(uint16_t)(info.width + 8) * (size_t)(uint16_t)(info.height + 8);
-            const size_t extra = (interleaved ? 128u : 0u) * (size_t)info.height * out_nc;
-            const size_t chunk = (size_t)info.width * out_nc * 8 * h_max * v_max;
-            if (mcu_h > (capacity * out_nc + extra) / chunk) FAIL(ZJ_DE_GPU, "the reference decoder panics on this geometry (output chunks exhausted, mcu.rs:354)");
+            const size_t extra = (interleaved ? 128u : 0u) * (size_t)info.height * g.out_nc;
+            const size_t chunk = (size_t)info.width * g.out_nc * 8 * h_max * v_max;
+            if (mcu_h > (capacity * g.out_nc + extra) / chunk) FAIL(ZJ_DE_GPU, "the reference decoder panics on this geometry (output chunks exhausted, mcu.rs:354)");
         }
         // whole-image planes: strip s of component z lives at s * strip_len[z] (== mcu_prog.rs layout)
-        size_t strip_len[3] = {0, 0, 0};
-        for (size_t pos = 0; pos < components.size() && pos < 3; pos++) {
-            plane_len[pos] = 0;
-            if (std::min(out_nc - 1, pos) == pos) {  // mcu.rs:244
-                strip_len[pos] = component_capacity * components[pos].vertical_sample * components[pos].horizontal_sample * bias;
-                plane_len[pos] = strip_len[pos] * mcu_h;
-                planes[pos].ensure_zeroed(plane_len[pos], have_device);
-            }
-        }
-        BitStream stream;
-        int16_t tmp[64];
-        for (size_t strip = 0; strip < mcu_h; strip++) {
-            for (size_t v = 0; v < bias; v++) {
-                for (size_t j = 0; j < mcu_w; j++) {
-                    for (size_t pos = 0; pos < in_components(); pos++) {
-                        Component &component = components[pos];
-                        const HuffmanTable &dc_table = dc_tables[component.dc_huff_table & 3];
-                        if (!dc_table.present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No DC table for component %s", comp_debug(component.component_id)));
-                        const HuffmanTable &ac_table = ac_tables[component.ac_huff_table & 3];
-                        if (!ac_table.present) FAIL(ZJ_DE_HUFFMAN_DECODE, fmt("No AC table for component %s", comp_debug(component.component_id)));
-                        for (size_t v_samp = 0; v_samp < component.vertical_sample; v_samp++) {
-                            for (size_t h_samp = 0; h_samp < component.horizontal_sample; h_samp++) {
-                                if (std::min(out_nc - 1, pos) == pos) {
-                                    // mcu.rs:293-312
-                                    const size_t is_y = component.component_id == ID_Y ? 1 : 0;
-                                    const size_t y_offset = is_y * v * (hv_width_stride + (hv_width_stride * (component.vertical_sample - 1)));
-                                    const size_t another_stride = (width_stride * v_samp * (is_hv ? 0 : 1)) + hv_width_stride * v_samp * (is_hv ? 1 : 0);
-                                    const size_t yet_another_stride = (is_hv ? 1 : 0) * (width_stride >> 2) * v * (component.component_id != ID_Y ? 1 : 0);
-                                    const size_t start = (j * 64 * component.horizontal_sample) + (h_samp * 64) + another_stride + y_offset + yet_another_stride;
-                                    if (start + 64 > strip_len[pos]) FAIL(ZJ_DE_GPU, "the reference decoder panics here (block index out of range, mcu.rs:314)");
-                                    stream.decode_mcu_block(reader, dc_table, ac_table, planes[pos].p + strip * strip_len[pos] + start, component.dc_pred);
-                                } else {
-                                    stream.decode_mcu_block(reader, dc_table, ac_table, tmp, component.dc_pred);
-                                }
-                            }
-                        }
-                        todo = todo - 1;  // wrapping_sub, once per COMPONENT (Q8)
-                        if (todo == 0) handle_rst(stream);
-                        if (stream.has_marker) {  // mcu.rs:337-348
-                            if (stream.marker.kind == M_EOI) break;
-                            if (stream.marker.kind == M_RST) continue;
-                            parse_marker_inner(stream.marker, reader);
-                        }
-                    }
+        last_entropy_segments = 0;
+        size_t threads = entropy_threads ? entropy_threads : (options.num_threads ? options.num_threads : std::thread::hardware_concurrency());
+        if (threads == 0) threads = 1;
+        const size_t total = mcu_w * mcu_h * bias;
+        // (zeroing 200 MB of planes of an 8192^2 image takes as long as entropy-decoding it on 8 threads: split it too)
+        auto zero_planes = [&]() {
+            size_t bytes = 0;
+            for (size_t pos = 0; pos < components.size() && pos < 3; pos++) {
+                plane_len[pos] = 0;
+                g.strip_len[pos] = 0;
+                if (std::min(g.out_nc - 1, pos) == pos) {  // mcu.rs:244
+                    g.strip_len[pos] = component_capacity * components[pos].vertical_sample * components[pos].horizontal_sample * bias;
+                    plane_len[pos] = g.strip_len[pos] * mcu_h;
+                    bytes += plane_len[pos] * 2;
                 }
             }
+            const bool split = threads > 1 && bytes >= ((size_t)8 << 20);
+            for (size_t pos = 0; pos < 3; pos++)
+                if (plane_len[pos]) planes[pos].ensure_zeroed(plane_len[pos], have_device, !split);
+            if (!split) return;
+            const size_t CH = (size_t)1 << 20;   // bytes per piece
+            std::vector<std::pair<char *, size_t>> pieces;
+            for (size_t pos = 0; pos < 3; pos++)
+                for (size_t o = 0; o < plane_len[pos] * 2; o += CH) pieces.emplace_back((char *)planes[pos].p + o, std::min(CH, plane_len[pos] * 2 - o));
+            std::atomic<size_t> next{0};
+            auto work = [&]() { for (size_t i; (i = next.fetch_add(1)) < pieces.size();) memset(pieces[i].first, 0, pieces[i].second); };
+            std::vector<std::thread> pool;
+            for (size_t t = 1; t < threads; t++) pool.emplace_back(work);
+            work();
+            for (auto &t : pool) t.join();
+        };
+        zero_planes();
+        ScanState st;
+        for (size_t pos = 0; pos < g.ncomp && pos < 3; pos++) st.dc_pred[pos] = components[pos].dc_pred;
+        st.todo = todo;
+        // worth the thread start-up only for scans of some size (about 0.1 ms of Huffman work per 4096 blocks)
+        if (threads > 1 && restart_interval > 0 && todo == restart_interval && total >= 2 * restart_interval &&
+            reader.len - std::min(reader.len, reader.pos) >= (size_t)64 * 1024) {
+            if (baseline_parallel(reader, st, g, threads)) return;
+            zero_planes();   // some interval did not end like a conformant one: the reference's loop decides what comes out
         }
+        baseline_mcus<false>(reader, st, g, 0, total, false);
+        for (size_t pos = 0; pos < g.ncomp && pos < 3; pos++) components[pos].dc_pred = st.dc_pred[pos];
+        todo = st.todo;
     }
 
     // ---------------------------------------------------------------- progressive entropy stage (mcu_prog.rs)
@@ -1208,6 +1362,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
     if (o) opt = *o; else zj_options_default(&opt);
     size_t nthreads = opt.num_threads ? opt.num_threads : std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 1;
+    const size_t per_image_threads = n ? std::max<size_t>(1, nthreads / n) : 1;
     if (nthreads > n) nthreads = n;
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
@@ -1223,6 +1378,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
         }
         if (d) { d->options = opt; d->user_out_cs = opt.out_colorspace; d->clear_error(); }
         else d = zj_decoder_new(&opt);
+        if (d) d->entropy_threads = per_image_threads;   // the host threads left over when there are fewer images than threads
         for (;;) {
             const size_t i = next.fetch_add(1);
             if (i >= n) break;
@@ -1258,6 +1414,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
     for (auto &t : pool) t.join();
     return failed.load();
 }
+ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d) { return d ? d->last_entropy_segments : 0; }
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d) { return d ? d->err_kind : ZJ_DE_NONE; }
 ZJ_API const char *zj_decoder_error(const zj_decoder *d) { return d ? d->err_display.c_str() : ""; }
 

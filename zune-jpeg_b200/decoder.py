@@ -230,6 +230,11 @@ class Decoder:
             planes.append(a)
         return img, planes
 
+    def entropy_segments(self) -> int:
+        """Restart intervals the last decode entropy-decoded side by side on `num_threads` host threads (0 = the
+        reference's sequential loop, mcu.rs:253-351, ran instead)."""
+        return int(self._lib.zj_decoder_entropy_segments(self._h))
+
     # ---- queries
     def info(self):
         """Decoder::info (decoder.rs:210): None until headers were parsed."""
