@@ -296,3 +296,30 @@ def test_reference_fixture_geometries(w, h, mode):
     these outputs, here they must equal the oracle byte for byte."""
     rng = np.random.default_rng(hash((w, h, mode)) & 0xFFFF)
     assert _run_case(rng, w, h, mode, 0, 0) == "ok"
+
+
+@pytest.mark.parametrize("name,w,h,sub,prog,gray,out_cs,rst", [
+    ("c3_444", 4096, 4096, "444", False, False, 0, 0),
+    ("c3_gray", 4096, 4096, "444", False, True, 1, 0),
+    ("c4", 1920, 1080, "422", True, False, 0, 0),
+    ("c5", 8192, 8192, "420", False, False, 5, 1),
+])
+def test_baseline_configs_from_jpeg_bytes(name, w, h, sub, prog, gray, out_cs, rst):
+    """BASELINE configs[2..4] at full size, from JPEG bytes: Decoder.decode_buffer (host stage on 4 threads -- for c5 that is
+    the restart-interval-parallel entropy decode -- then the GPU) against the oracle fed with the planes of the sequential
+    host stage."""
+    import os
+    import jpeg_util
+    from zune_jpeg_b200.decoder import ColorSpace, Decoder, ZuneJpegOptions
+    data = jpeg_util.synth_jpeg(7, w, h, sub, 90, prog, gray, rst)
+    opts = ZuneJpegOptions().set_out_colorspace(ColorSpace(out_cs))
+    seq = Decoder.new_with_options(opts.set_num_threads(1))
+    img, planes = seq.decode_coefficients(data)
+    for z in range(img.n_comp):
+        img.comp[z].coeff = planes[z].ctypes.data if planes[z].size else None
+    want = oracle.reconstruct(img, threads=os.cpu_count() or 1)
+    d = Decoder.new_with_options(opts.set_num_threads(4))
+    got = np.frombuffer(d.decode_buffer(data), np.uint8)
+    assert got.size == w * h * ColorSpace(out_cs).num_components()
+    assert np.array_equal(got, want)
+    assert (d.entropy_segments() > 0) == bool(rst)
