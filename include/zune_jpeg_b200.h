@@ -118,6 +118,15 @@ ZJ_API int zj_validate_image(const zj_image *img);
 ZJ_API int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
                               uint8_t *const *out, const size_t *out_len);
 
+/* The same call in two halves, for callers that have host work to do meanwhile (mcu.rs:230-369 entropy-decodes strip k+1
+ * while its pool post-processes strip k): _submit queues the uploads, kernels and downloads and returns; the planes and the
+ * outputs must stay untouched until _finish(pending) has returned, which waits (the thread sleeps, it does not spin),
+ * releases `pending` and reports the status of the whole call.  A failed _submit leaves nothing to finish. */
+typedef struct zj_pending zj_pending;
+ZJ_API int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, size_t n,
+                                     uint8_t *const *out, const size_t *out_len, zj_pending **pending);
+ZJ_API int zj_gpu_reconstruct_finish(zj_pending *pending);
+
 /* DEVICE entry point: coefficient planes and outputs already live in the memory of `device`.
  * Asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream); no host<->device pixel traffic.
  * Device coefficient planes must start on a 16-byte boundary (ZJ_ERR_INVALID_ARG otherwise; cudaMalloc'ed memory
@@ -225,8 +234,8 @@ ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t le
 ZJ_API void zj_buffer_free(uint8_t *p);
 /* Batch front door (the reference has none: it parallelises the strips of ONE image, mcu.rs:230-369): n JPEGs are
  * decoded by `o->num_threads` host threads (0 = one per hardware thread), one image per thread at a time; each thread
- * runs the host stage and hands its planes to zj_gpu_reconstruct, so entropy decoding of some images overlaps transfer
- * and reconstruction of others.  out[i] non-NULL on entry = caller buffer of out_len[i] bytes (pinned memory copies
+ * runs the host stage, hands its planes to zj_gpu_reconstruct_submit and starts on its next image (a second set of planes)
+ * while the GPU works, so entropy decoding overlaps transfer and reconstruction of this thread's and the others' images.  out[i] non-NULL on entry = caller buffer of out_len[i] bytes (pinned memory copies
  * fastest); NULL = malloc'ed here (zj_buffer_free).  status[i] = per-image zj_status; returns the number of failed
  * images (0 = all decoded) or a negative zj_status for invalid arguments. */
 ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,

@@ -78,6 +78,8 @@ SYMBOLS = {
     "zj_output_size": (C.c_size_t, [C.POINTER(ZjImage)]),
     "zj_validate_image": (C.c_int, [C.POINTER(ZjImage)]),
     "zj_gpu_reconstruct": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
+    "zj_gpu_reconstruct_submit": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t), _PP]),
+    "zj_gpu_reconstruct_finish": (C.c_int, [_P]),
     "zj_gpu_reconstruct_device": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
     "zj_batch_create": (C.c_int, [C.c_int, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t), _PP]),
     "zj_batch_run": (C.c_int, [_P, _P]),

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "../../include/zune_jpeg_b200.h"
@@ -384,10 +385,39 @@ int zj_gpu_reconstruct_device(int device, void *stream, const zj_image *imgs, si
     return rc;
 }
 
-// Host entry point: stage planes H2D, run, copy pixels D2H.  Images are processed in sub-batches on two
-// internal streams so that the copies of one sub-batch overlap the kernels of the other.
-int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n, uint8_t *const *out, const size_t *out_len)
+// Host entry point: stage planes H2D, run, copy pixels D2H.  Images are processed in sub-batches on internal streams so
+// that the copies of one sub-batch overlap the kernels of the other.  Split in two halves: zj_gpu_reconstruct_submit queues
+// everything and returns while the GPU works (the caller's planes and outputs stay in use), zj_gpu_reconstruct_finish waits
+// and releases the per-call state; zj_gpu_reconstruct = both.
+struct zj_pending {
+    int device = 0;
+    int ns = 0;
+    cudaStream_t st[4] = {};
+    cudaStream_t user = nullptr;
+    cudaEvent_t done[4] = {};
+    std::vector<zj_batch *> batches;
+};
+
+int zj_gpu_reconstruct_finish(zj_pending *p)
 {
+    if (!p) return ZJ_ERR_INVALID_ARG;
+    int rc = set_device(p->device);
+    for (int k = 0; k < p->ns && rc == ZJ_OK; k++) {
+        // a blocking-sync event: the host thread sleeps instead of spinning, its core is free for another thread's Huffman work
+        cudaError_t e = p->done[k] ? cudaEventSynchronize(p->done[k]) : cudaStreamSynchronize(p->st[k]);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize");
+    }
+    for (int k = 0; k < p->ns; k++) if (p->done[k]) cudaEventDestroy(p->done[k]);
+    for (zj_batch *b : p->batches) zj_batch_destroy(b);
+    if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize(p->user); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(user)"); }
+    delete p;
+    return rc;
+}
+
+int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, size_t n, uint8_t *const *out, const size_t *out_len, zj_pending **pending)
+{
+    if (!pending) return ZJ_ERR_INVALID_ARG;
+    *pending = nullptr;
     if ((!imgs || !out || !out_len) && n) return ZJ_ERR_INVALID_ARG;
     int rc = set_device(device);
     if (rc) return rc;
@@ -424,10 +454,16 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
     CU(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     CU(cudaEventRecord(ev_in, user));
     for (int k = 0; k < NS; k++) CU(cudaStreamWaitEvent(st[k], ev_in, 0));
+    cudaEventDestroy(ev_in);   // (released once the recorded work has completed)
+
+    zj_pending *pd = new (std::nothrow) zj_pending;
+    if (!pd) return ZJ_ERR_OOM;
+    pd->device = device;
+    pd->ns = NS;
+    pd->user = user;
+    for (int k = 0; k < NS; k++) pd->st[k] = st[k];
 
     const size_t budget = (size_t)(env_mb ? std::max(16, atoi(env_mb)) : 256) << 20;  // device staging per sub-batch
-    std::vector<void *> to_free;
-    std::vector<zj_batch *> batches;
     size_t i = 0;
     int which = 0;
     rc = ZJ_OK;
@@ -471,7 +507,7 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
         zj_batch *b = nullptr;
         rc = batch_create_impl(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b, true, s);
         if (rc != ZJ_OK) break;
-        batches.push_back(b);
+        pd->batches.push_back(b);
         rc = zj_batch_run(b, s);
         if (rc != ZJ_OK) break;
         for (size_t k = i; k < j; k++) {
@@ -480,15 +516,25 @@ int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n,
         }
         i = j;
     }
-    for (int k = 0; k < NS; k++) {
-        cudaError_t e = cudaStreamSynchronize(st[k]);
-        if (e != cudaSuccess && rc == ZJ_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    if (rc == ZJ_OK) {
+        for (int k = 0; k < NS; k++) {
+            if (cudaEventCreateWithFlags(&pd->done[k], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { pd->done[k] = nullptr; cudaGetLastError(); continue; }
+            if (cudaEventRecord(pd->done[k], st[k]) != cudaSuccess) { cudaEventDestroy(pd->done[k]); pd->done[k] = nullptr; cudaGetLastError(); }
+        }
+        *pending = pd;
+        return ZJ_OK;
     }
-    for (void *p : to_free) cudaFree(p);
-    for (zj_batch *b : batches) zj_batch_destroy(b);
-    cudaEventDestroy(ev_in);
-    if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize(user); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(user)"); }
-    return rc;
+    const int rc_submit = rc;
+    zj_gpu_reconstruct_finish(pd);   // waits for what was queued, releases the descriptors
+    return rc_submit;
+}
+
+int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n, uint8_t *const *out, const size_t *out_len)
+{
+    zj_pending *pd = nullptr;
+    int rc = zj_gpu_reconstruct_submit(device, stream, imgs, n, out, out_len, &pd);
+    if (rc != ZJ_OK) return rc;
+    return zj_gpu_reconstruct_finish(pd);
 }
 
 // ------------------------------------------------------------------------------------- memory helpers

@@ -234,7 +234,14 @@ struct BitStream {  // src/bitstream.rs:94-114
         return (~((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) | 0x7F7F7F7Fu)) != 0;
     }
     // bitstream.rs:159-261
-    void refill(Cursor &r)
+    // (the test that decides whether anything happens is kept inline in front of the out-of-line body: it is evaluated once
+    // per Huffman symbol and is false for most of them)
+    inline __attribute__((always_inline)) void refill(Cursor &r)
+    {
+        if (__builtin_expect(bits_left > 32 && !has_marker, 1)) return;
+        refill_body(r);
+    }
+    __attribute__((noinline)) void refill_body(Cursor &r)
     {
         if (bits_left <= 32 && !has_marker) {
             const size_t position = r.pos;
@@ -844,7 +851,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
     };
     struct BaselineGeom {
         size_t mcu_w = 0, mcu_h = 0, bias = 1, width_stride = 0, hv_width_stride = 0, out_nc = 0, ncomp = 0;
-        bool is_hv = false;
+        bool is_hv = false, zero_per_strip = false;
         size_t strip_len[3] = {0, 0, 0};
     };
     struct SegmentAbnormal {};   // the interval did not end the way a conformant one does: redo the scan sequentially
@@ -866,6 +873,12 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         const size_t per_strip = g.bias * g.mcu_w;
         for (size_t m = first; m < last; m++) {
             const size_t strip = m / per_strip, v = (m - strip * per_strip) / g.mcu_w, j = m - strip * per_strip - v * g.mcu_w;
+            if (!SEGMENT && g.zero_per_strip && m == strip * per_strip) {
+                // the planes start out zeroed (mcu.rs:238-250 allocates fresh zeroed strip buffers): done strip by strip right
+                // before the strip is decoded, so the blocks are still in cache when the coefficients are written
+                for (size_t pos = 0; pos < 3; pos++)
+                    if (g.strip_len[pos]) memset(planes[pos].p + strip * g.strip_len[pos], 0, g.strip_len[pos] * 2);
+            }
             for (size_t pos = 0; pos < g.ncomp; pos++) {
                 const Component &component = components[pos];
                 const HuffmanTable &dc_table = dc_tables[component.dc_huff_table & 3];
@@ -1034,22 +1047,18 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         size_t threads = entropy_threads ? entropy_threads : (options.num_threads ? options.num_threads : std::thread::hardware_concurrency());
         if (threads == 0) threads = 1;
         const size_t total = mcu_w * mcu_h * bias;
-        // (zeroing 200 MB of planes of an 8192^2 image takes as long as entropy-decoding it on 8 threads: split it too)
-        auto zero_planes = [&]() {
-            size_t bytes = 0;
-            for (size_t pos = 0; pos < components.size() && pos < 3; pos++) {
-                plane_len[pos] = 0;
-                g.strip_len[pos] = 0;
-                if (std::min(g.out_nc - 1, pos) == pos) {  // mcu.rs:244
-                    g.strip_len[pos] = component_capacity * components[pos].vertical_sample * components[pos].horizontal_sample * bias;
-                    plane_len[pos] = g.strip_len[pos] * mcu_h;
-                    bytes += plane_len[pos] * 2;
-                }
+        for (size_t pos = 0; pos < components.size() && pos < 3; pos++) {
+            plane_len[pos] = 0;
+            g.strip_len[pos] = 0;
+            if (std::min(g.out_nc - 1, pos) == pos) {  // mcu.rs:244
+                g.strip_len[pos] = component_capacity * components[pos].vertical_sample * components[pos].horizontal_sample * bias;
+                plane_len[pos] = g.strip_len[pos] * mcu_h;
+                planes[pos].ensure_zeroed(plane_len[pos], have_device, false);
             }
-            const bool split = threads > 1 && bytes >= ((size_t)8 << 20);
-            for (size_t pos = 0; pos < 3; pos++)
-                if (plane_len[pos]) planes[pos].ensure_zeroed(plane_len[pos], have_device, !split);
-            if (!split) return;
+        }
+        // zeroing all planes at once, for the interval-parallel form (whose intervals start anywhere inside a strip): split over
+        // the threads too -- 200 MB of planes of an 8192^2 image take as long to clear as to entropy-decode on 8 threads
+        auto zero_planes = [&]() {
             const size_t CH = (size_t)1 << 20;   // bytes per piece
             std::vector<std::pair<char *, size_t>> pieces;
             for (size_t pos = 0; pos < 3; pos++)
@@ -1057,20 +1066,21 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             std::atomic<size_t> next{0};
             auto work = [&]() { for (size_t i; (i = next.fetch_add(1)) < pieces.size();) memset(pieces[i].first, 0, pieces[i].second); };
             std::vector<std::thread> pool;
-            for (size_t t = 1; t < threads; t++) pool.emplace_back(work);
+            for (size_t t = 1; t < threads && t < pieces.size(); t++) pool.emplace_back(work);
             work();
             for (auto &t : pool) t.join();
         };
-        zero_planes();
         ScanState st;
         for (size_t pos = 0; pos < g.ncomp && pos < 3; pos++) st.dc_pred[pos] = components[pos].dc_pred;
         st.todo = todo;
         // worth the thread start-up only for scans of some size (about 0.1 ms of Huffman work per 4096 blocks)
         if (threads > 1 && restart_interval > 0 && todo == restart_interval && total >= 2 * restart_interval &&
             reader.len - std::min(reader.len, reader.pos) >= (size_t)64 * 1024) {
+            zero_planes();
             if (baseline_parallel(reader, st, g, threads)) return;
-            zero_planes();   // some interval did not end like a conformant one: the reference's loop decides what comes out
+            // some interval did not end like a conformant one: the reference's loop decides what comes out
         }
+        g.zero_per_strip = true;
         baseline_mcus<false>(reader, st, g, 0, total, false);
         for (size_t pos = 0; pos < g.ncomp && pos < 3; pos++) components[pos].dc_pred = st.dc_pred[pos];
         todo = st.todo;
@@ -1370,7 +1380,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
     // image and thread costs more than decoding it, and both serialise in the driver
     static std::mutex idle_mu;
     static std::vector<zj_decoder *> idle;
-    auto worker = [&]() {
+    auto take_decoder = [&]() -> zj_decoder * {
         zj_decoder *d = nullptr;
         {
             std::lock_guard<std::mutex> lock(idle_mu);
@@ -1379,9 +1389,35 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
         if (d) { d->options = opt; d->user_out_cs = opt.out_colorspace; d->clear_error(); }
         else d = zj_decoder_new(&opt);
         if (d) d->entropy_threads = per_image_threads;   // the host threads left over when there are fewer images than threads
+        return d;
+    };
+    auto give_back = [&](zj_decoder *d) {
+        if (!d) return;
+        {
+            std::lock_guard<std::mutex> lock(idle_mu);
+            if (idle.size() < 512) { idle.push_back(d); return; }
+        }
+        zj_decoder_free(d);
+    };
+    // A worker alternates between two decoders (two sets of pinned planes): while the GPU uploads, reconstructs and
+    // downloads image i from the planes of one, the thread entropy-decodes its next image into the planes of the other.
+    auto worker = [&]() {
+        zj_decoder *dec[2] = {take_decoder(), nullptr};
+        struct InFlight { zj_pending *pd = nullptr; size_t i = 0; uint8_t *dst = nullptr; size_t need = 0; bool mine = false; } fl;
+        auto settle = [&]() {   // wait for the image in flight and publish its result
+            if (!fl.pd) return;
+            const int rc = zj_gpu_reconstruct_finish(fl.pd);
+            fl.pd = nullptr;
+            if (rc == ZJ_OK) { out[fl.i] = fl.dst; out_len[fl.i] = fl.need; }
+            else { if (fl.mine) free(fl.dst); if (fl.mine || !out[fl.i]) out[fl.i] = nullptr; out_len[fl.i] = 0; failed++; }
+            status[fl.i] = rc;
+        };
+        int cur = 0;
         for (;;) {
             const size_t i = next.fetch_add(1);
             if (i >= n) break;
+            if (!dec[cur]) dec[cur] = take_decoder();
+            zj_decoder *d = dec[cur];
             if (!d) { status[i] = ZJ_ERR_OOM; failed++; continue; }
             zj_image img;
             int rc = (!bufs[i] && lens[i]) ? ZJ_ERR_INVALID_ARG : zj_decoder_decode_coefficients(d, bufs[i], lens[i], &img);
@@ -1397,16 +1433,23 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
                 if (dst) { if (out_len[i] < need) rc = ZJ_ERR_SHORT_OUTPUT; }
                 else { dst = (uint8_t *)malloc(need); mine = true; if (!dst) rc = ZJ_ERR_OOM; }
             }
-            if (rc == ZJ_OK) rc = zj_gpu_reconstruct(opt.device, nullptr, &img, 1, &dst, &need);
-            if (rc == ZJ_OK) { out[i] = dst; out_len[i] = need; }
-            else { if (mine) free(dst); if (mine || !out[i]) out[i] = nullptr; out_len[i] = 0; failed++; }
-            status[i] = rc;
+            settle();   // the previous image (its planes are the ones this thread decodes into next)
+            zj_pending *pd = nullptr;
+            if (rc == ZJ_OK) rc = zj_gpu_reconstruct_submit(opt.device, nullptr, &img, 1, &dst, &need, &pd);
+            if (rc == ZJ_OK) {
+                fl.pd = pd; fl.i = i; fl.dst = dst; fl.need = need; fl.mine = mine;
+                cur ^= 1;
+            } else {
+                if (mine) free(dst);
+                if (mine || !out[i]) out[i] = nullptr;
+                out_len[i] = 0;
+                failed++;
+                status[i] = rc;
+            }
         }
-        if (d) {
-            std::lock_guard<std::mutex> lock(idle_mu);
-            if (idle.size() < 256) { idle.push_back(d); d = nullptr; }
-        }
-        zj_decoder_free(d);
+        settle();
+        give_back(dec[0]);
+        give_back(dec[1]);
     };
     std::vector<std::thread> pool;
     for (size_t t = 1; t < nthreads; t++) pool.emplace_back(worker);
