@@ -478,6 +478,18 @@ def run_ours(args):
             single[label] = {"threads": nt, "intervals_side_by_side": int(seg), "host_stage_ms": round(best_h * 1e3, 2),
                              "total_ms": round(best_t * 1e3, 2), "MP/s": round(w * h / 1e6 / best_t, 1)}
         decode["single_image"] = single
+        # the same batch with the entropy stage on the GPU as well (zj_decode_batch_gpu: one restart interval per GPU thread)
+        stats = {}
+        decode_batch(jpegs[:min(nd, 8)], opts, threads=threads, out=outs[:min(nd, 8)], gpu_entropy=True, stats=stats)   # warm-up
+        t0 = time.perf_counter()
+        res = decode_batch(jpegs, opts, threads=threads, out=outs, gpu_entropy=True, stats=stats)
+        dtg = time.perf_counter() - t0
+        if any(not isinstance(r, int) for r in res):
+            raise SystemExit("bench.py: zj_decode_batch_gpu failed")
+        if not args.no_check and not np.array_equal(outs[0], want):
+            raise SystemExit("bench.py: zj_decode_batch_gpu output differs from the oracle")
+        decode["gpu_entropy"] = {"value": round(nd * w * h / 1e6 / dtg, 2), "unit": "MP/s", "images": nd, "images_entropy_decoded_on_gpu": stats.get("gpu_entropy"),
+                                 "seconds": round(dtg, 3), "how": "zj_decode_batch_gpu: JPEG files uploaded, restart intervals entropy-decoded one per GPU thread into device planes, reconstructed, pixels downloaded to pinned host memory"}
 
     # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
     peaks = {}

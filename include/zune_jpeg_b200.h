@@ -240,6 +240,14 @@ ZJ_API void zj_buffer_free(uint8_t *p);
  * images (0 = all decoded) or a negative zj_status for invalid arguments. */
 ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                            uint8_t **out, size_t *out_len, int *status);
+/* The same call with the entropy stage on the GPU too, for the JPEGs that allow it: baseline scans with restart markers (DRI)
+ * whose every interval ends the way the reference's sequential loop (src/mcu.rs:253-351, 386-418) ends it.  Their files are
+ * uploaded instead of their coefficient planes, one GPU thread per restart interval runs the reference's bit reader and MCU
+ * loop (src/bitstream.rs:159-402) into device planes, which are reconstructed in place.  All other images (no DRI,
+ * progressive, header errors, an interval that ends differently) take the zj_decode_batch route, so pixels, statuses and
+ * errors are those of zj_decode_batch.  *n_gpu_entropy (may be NULL) = images whose entropy stage ran on the GPU. */
+ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                               uint8_t **out, size_t *out_len, int *status, size_t *n_gpu_entropy);
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d);                 /* zj_decode_error_kind                */
 ZJ_API const char *zj_decoder_error(const zj_decoder *d);              /* Display text of the DecodeErrors    */
 

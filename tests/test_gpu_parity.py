@@ -323,3 +323,42 @@ def test_baseline_configs_from_jpeg_bytes(name, w, h, sub, prog, gray, out_cs, r
     assert got.size == w * h * ColorSpace(out_cs).num_components()
     assert np.array_equal(got, want)
     assert (d.entropy_segments() > 0) == bool(rst)
+
+
+def test_gpu_entropy_decode_matches_host_stage():
+    """zj_decode_batch_gpu: restart intervals entropy-decoded one per GPU thread (zj_entropy.cu) give the pixels of the host
+    stage (the reference's sequential loop); images without restart markers, progressive ones, streams whose declared DRI does
+    not match their markers and damaged streams silently take the host route and still give identical results / errors."""
+    import jpeg_util
+    from zune_jpeg_b200.decoder import ColorSpace, DecodeErrors, decode_batch, ZuneJpegOptions
+    cases = []   # (jpeg, expected to run on the GPU)
+    for i, (w, h, sub, gray, rows, q) in enumerate([(1024, 768, "420", False, 1, 90), (1000, 1016, "420", False, 2, 75), (1280, 720, "422", False, 1, 85),
+                                                     (800, 600, "444", False, 3, 95), (2048, 1024, "444", True, 1, 90), (3840, 2160, "420", False, 1, 98),
+                                                     (640, 480, "440", False, 1, 60)]):
+        if sub == "440":
+            continue
+        cases.append((jpeg_util.synth_jpeg(30 + i, w, h, sub, q, False, gray, rows), True))
+    cases.append((jpeg_util.synth_jpeg(40, 800, 608, "420", 90), False))                       # no DRI
+    cases.append((jpeg_util.synth_jpeg(41, 800, 608, "422", 90, True), False))                 # progressive
+    base = jpeg_util.synth_jpeg(42, 1024, 512, "420", 80, restart_rows=1)
+    i = base.index(b"\xff\xdd")
+    cases.append((base[:i + 4] + bytes([0, 7]) + base[i + 6:], False))                         # DRI does not match the markers (Q8 territory)
+    cut = bytearray(base); del cut[len(cut) // 2:]
+    cases.append((bytes(cut), False))                                                          # truncated
+    flip = bytearray(base); flip[len(flip) // 2] ^= 0x10
+    cases.append((bytes(flip), None))                                                          # damaged entropy data: either route
+    cases.append((bytes([0xff, 0xd8, 0xa4]), False))                                           # header error
+    jpegs = [c[0] for c in cases]
+    for out_cs in (ColorSpace.RGB, ColorSpace.RGBA, ColorSpace.GRAYSCALE):
+        opts = ZuneJpegOptions().set_out_colorspace(out_cs)
+        want = decode_batch(jpegs, opts, threads=4)
+        stats = {}
+        got = decode_batch(jpegs, opts, threads=4, gpu_entropy=True, stats=stats)
+        for k, (g, w_) in enumerate(zip(got, want)):
+            if isinstance(w_, DecodeErrors):
+                assert isinstance(g, DecodeErrors) and g.status == w_.status, k
+            else:
+                assert g == w_, f"image {k} out_cs={out_cs}"
+        sure = sum(1 for c in cases if c[1] is True)
+        maybe = sum(1 for c in cases if c[1] is None)
+        assert sure <= stats["gpu_entropy"] <= sure + maybe, stats

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <string>
 #include <thread>
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include "../../include/zune_jpeg_b200.h"
+#include "zj_entropy.h"
 
 namespace {
 
@@ -999,7 +1001,8 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         return true;
     }
 
-    void decode_baseline(Cursor &reader)
+    // Everything decode_baseline settles before its MCU loop (mcu.rs:139-250): checks, strip geometry, plane sizes.
+    void baseline_setup(BaselineGeom &g)
     {
         check_component_dimensions();
         check_tables();
@@ -1028,7 +1031,6 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             bias = 1;
         }
         const size_t component_capacity = mcu_w * 64;
-        BaselineGeom g;
         g.mcu_w = mcu_w; g.mcu_h = mcu_h; g.bias = bias;
         g.is_hv = sub_sample_ratio == SS_HV;
         g.out_nc = out_components(options.out_colorspace);
@@ -1043,19 +1045,25 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             if (mcu_h > (capacity * g.out_nc + extra) / chunk) FAIL(ZJ_DE_GPU, "the reference decoder panics on this geometry (output chunks exhausted, mcu.rs:354)");
         }
         // whole-image planes: strip s of component z lives at s * strip_len[z] (== mcu_prog.rs layout)
-        last_entropy_segments = 0;
-        size_t threads = entropy_threads ? entropy_threads : (options.num_threads ? options.num_threads : std::thread::hardware_concurrency());
-        if (threads == 0) threads = 1;
-        const size_t total = mcu_w * mcu_h * bias;
+        for (size_t pos = 0; pos < 3; pos++) { plane_len[pos] = 0; g.strip_len[pos] = 0; }
         for (size_t pos = 0; pos < components.size() && pos < 3; pos++) {
-            plane_len[pos] = 0;
-            g.strip_len[pos] = 0;
             if (std::min(g.out_nc - 1, pos) == pos) {  // mcu.rs:244
                 g.strip_len[pos] = component_capacity * components[pos].vertical_sample * components[pos].horizontal_sample * bias;
                 plane_len[pos] = g.strip_len[pos] * mcu_h;
-                planes[pos].ensure_zeroed(plane_len[pos], have_device, false);
             }
         }
+    }
+
+    void decode_baseline(Cursor &reader)
+    {
+        BaselineGeom g;
+        baseline_setup(g);
+        last_entropy_segments = 0;
+        size_t threads = entropy_threads ? entropy_threads : (options.num_threads ? options.num_threads : std::thread::hardware_concurrency());
+        if (threads == 0) threads = 1;
+        const size_t total = g.mcu_w * g.mcu_h * g.bias;
+        for (size_t pos = 0; pos < 3; pos++)
+            if (plane_len[pos]) planes[pos].ensure_zeroed(plane_len[pos], have_device, false);
         // zeroing all planes at once, for the interval-parallel form (whose intervals start anywhere inside a strip): split over
         // the threads too -- 200 MB of planes of an 8192^2 image take as long to clear as to entropy-decode on 8 threads
         auto zero_planes = [&]() {
@@ -1084,6 +1092,54 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         baseline_mcus<false>(reader, st, g, 0, total, false);
         for (size_t pos = 0; pos < g.ncomp && pos < 3; pos++) components[pos].dc_pred = st.dc_pred[pos];
         todo = st.todo;
+    }
+
+    // ---------------------------------------------------------------- GPU form of the baseline entropy stage (zj_entropy.cu)
+    struct GpuPrep {
+        BaselineGeom g;
+        std::vector<uint32_t> seg_start;   // reader position at the start of every restart interval (+ one unused entry)
+        size_t n_seg = 0, total = 0;
+    };
+    // Headers are parsed (reader stands at the first entropy-coded byte).  True when the scan can be handed to the GPU: a
+    // baseline scan with restart markers in the state the interval-parallel forms start from.  Everything else -- and every
+    // error -- is left to the host stage, which then reports exactly what the reference reports.
+    bool gpu_entropy_prepare(const Cursor &reader, GpuPrep &pp)
+    {
+        if (is_progressive || restart_interval == 0 || todo != restart_interval) return false;
+        if (reader.len >= 0xFFFFFFF0ull) return false;
+        try { baseline_setup(pp.g); } catch (DecodeError &) { return false; }
+        const BaselineGeom &g = pp.g;
+        for (size_t pos = 0; pos < g.ncomp; pos++) {
+            const Component &c = components[pos];
+            if (c.dc_pred != 0 || !dc_tables[c.dc_huff_table & 3].present || !ac_tables[c.ac_huff_table & 3].present) return false;
+            if (g.strip_len[pos] > 0x7FFFFFFFull || plane_len[pos] > ((size_t)1 << 40)) return false;
+        }
+        pp.total = g.mcu_w * g.mcu_h * g.bias;
+        if (pp.total <= restart_interval || pp.total > 0x7FFFFFFFull) return false;
+        pp.n_seg = (pp.total + restart_interval - 1) / restart_interval;
+        std::vector<size_t> ends;
+        ends.reserve(pp.n_seg);
+        find_restart_markers(reader, reader.pos, pp.n_seg - 1, ends);
+        if (ends.size() < pp.n_seg - 1) return false;
+        pp.seg_start.resize(pp.n_seg + 1);
+        pp.seg_start[0] = (uint32_t)reader.pos;
+        for (size_t k = 1; k < pp.n_seg; k++) pp.seg_start[k] = (uint32_t)ends[k - 1];
+        pp.seg_start[pp.n_seg] = 0;
+        return true;
+    }
+    void gpu_entropy_tables(zj::EntTable *t) const   // [dc, ac] per component
+    {
+        for (size_t pos = 0; pos < in_components(); pos++) {
+            const HuffmanTable *src[2] = {&dc_tables[components[pos].dc_huff_table & 3], &ac_tables[components[pos].ac_huff_table & 3]};
+            for (int k = 0; k < 2; k++) {
+                zj::EntTable &d = t[2 * pos + k];
+                memcpy(d.lookup, src[k]->lookup, sizeof(d.lookup));
+                memcpy(d.ac_lookup, src[k]->ac_lookup, sizeof(d.ac_lookup));
+                memcpy(d.maxcode, src[k]->maxcode, sizeof(d.maxcode));
+                memcpy(d.offset, src[k]->offset, sizeof(d.offset));
+                memcpy(d.values, src[k]->values, sizeof(d.values));
+            }
+        }
     }
 
     // ---------------------------------------------------------------- progressive entropy stage (mcu_prog.rs)
@@ -1457,6 +1513,273 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
     for (auto &t : pool) t.join();
     return failed.load();
 }
+// Batch front door with the entropy stage on the GPU as well (zj_entropy.cu) for the JPEGs that allow it: baseline scans
+// with restart markers whose every interval ends the way the reference's sequential loop ends it.  Those upload their FILE
+// (not their coefficient planes: 12 MB instead of 201 MB for an 8192x8192 image), are entropy-decoded one restart interval per
+// GPU thread into device planes, reconstructed in place and downloaded.  Every other image -- no DRI, progressive, a header
+// error, one interval that ends differently -- goes through zj_decode_batch (host stage), so results and errors are the
+// same as there.
+ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                               uint8_t **out, size_t *out_len, int *status, size_t *n_gpu_entropy)
+{
+    if (n_gpu_entropy) *n_gpu_entropy = 0;
+    if ((!bufs || !lens || !out || !out_len || !status) && n) return ZJ_ERR_INVALID_ARG;
+    zj_options opt;
+    if (o) opt = *o; else zj_options_default(&opt);
+    size_t nthreads = opt.num_threads ? opt.num_threads : std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= opt.device) { cudaGetLastError(); return zj_decode_batch(o, bufs, lens, n, out, out_len, status); }
+
+    const bool trace = getenv("ZJ_GPU_ENTROPY_TRACE") != nullptr;   // phase times on stderr (adds synchronisation)
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
+    auto lap = [&](const char *what, cudaStream_t s) {
+        if (!trace) return;
+        if (s) cudaStreamSynchronize(s);
+        const double t = now();
+        fprintf(stderr, "[zj_decode_batch_gpu] %-28s %8.2f ms\n", what, t - t_mark);
+        t_mark = t;
+    };
+    // ---- headers + restart-marker scan of every image on the host threads
+    struct Item { zj_decoder *d = nullptr; zj_decoder::GpuPrep pp; bool gpu = false; size_t need = 0; zj_image img; };
+    std::vector<Item> items(n);
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t i; (i = next.fetch_add(1)) < n;) {
+                Item &it = items[i];
+                if (!bufs[i] || lens[i] == 0) continue;
+                it.d = zj_decoder_new(&opt);
+                if (!it.d) continue;
+                try {
+                    it.d->reset_state();
+                    Cursor cur{bufs[i], lens[i], 0};
+                    it.d->decode_headers_internal(cur);
+                    it.gpu = it.d->gpu_entropy_prepare(cur, it.pp);
+                    if (it.gpu) {
+                        it.d->fill_descriptor(&it.img);
+                        it.need = zj_output_size(&it.img);
+                        if (it.need == 0 || (out[i] && out_len[i] < it.need)) it.gpu = false;   // the host path reports it
+                        for (uint32_t z = 0; z < it.img.n_comp; z++) it.img.comp[z].coeff = it.img.comp[z].n_i16 ? (const int16_t *)16 : nullptr;
+                        if (it.gpu && zj_validate_image(&it.img) != ZJ_OK) it.gpu = false;
+                    }
+                } catch (DecodeError &) { it.gpu = false; }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < std::min(nthreads, n); t++) pool.emplace_back(work);
+        if (n) work();
+        for (auto &t : pool) t.join();
+    }
+
+    lap("headers + marker scan", nullptr);
+    // ---- GPU: sub-batches of as many images as fit the staging budget, two slots in flight
+    std::vector<char> on_gpu(n, 0);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    auto footprint = [&](const Item &it, size_t len) {
+        size_t b = al(len + 8) + al(sizeof(zj::EntImage)) + al(6 * sizeof(zj::EntTable)) + al((it.pp.n_seg + 1) * 4) + al(it.pp.n_seg) + al(it.need);
+        for (int z = 0; z < 3; z++) b += al(it.d->plane_len[z] * 2);
+        return b;
+    };
+    const char *env_mb = getenv("ZJ_GPU_ENTROPY_BUDGET_MB");
+    const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : 4096) << 20;
+    struct Slot {
+        cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
+        std::vector<size_t> idx; zj_batch *batch = nullptr;
+        std::vector<uint8_t> st_host; std::vector<size_t> st_off;
+    };
+    // the two slots' streams and device memory are kept between calls (allocating and freeing gigabytes costs 3-13 ms per
+    // call and synchronises the device); one call at a time uses them, a concurrent call works with slots of its own
+    struct SlotCache { Slot slot[2]; int device = -1; };
+    static std::mutex cache_mu;
+    static SlotCache cache;
+    SlotCache own;
+    std::unique_lock<std::mutex> cache_lock(cache_mu, std::try_to_lock);
+    SlotCache &sc = cache_lock.owns_lock() ? cache : own;
+    bool cuda_ok = cudaSetDevice(opt.device) == cudaSuccess;
+    if (cuda_ok && sc.device != opt.device) {
+        for (auto &sl : sc.slot) {
+            if (sl.mem) cudaFree(sl.mem);
+            if (sl.s) cudaStreamDestroy(sl.s);
+            sl = Slot{};
+        }
+        sc.device = opt.device;
+    }
+    Slot *slot = sc.slot;
+    int rc_fatal = ZJ_OK;
+    for (int k = 0; k < 2 && cuda_ok; k++)
+        if (!slot[k].s) cuda_ok = cudaStreamCreateWithFlags(&slot[k].s, cudaStreamNonBlocking) == cudaSuccess;
+    auto drain = [&](Slot &sl) {   // wait for the slot's downloads, publish its images
+        if (sl.idx.empty()) return;
+        const bool ok = cudaStreamSynchronize(sl.s) == cudaSuccess;
+        if (sl.batch) { zj_batch_destroy(sl.batch); sl.batch = nullptr; }
+        for (size_t i : sl.idx) if (on_gpu[i] == 1) on_gpu[i] = ok ? 2 : 0;
+        sl.idx.clear();
+    };
+    std::vector<uint8_t *> malloced(n, nullptr);
+    size_t i0 = 0;
+    int which = 0;
+    while (cuda_ok && i0 < n) {
+        // next run of images for this slot
+        Slot &sl = slot[which];
+        drain(sl);
+        size_t bytes = 0, i1 = i0;
+        std::vector<size_t> take;
+        while (i1 < n) {
+            const Item &it = items[i1];
+            if (it.gpu) {
+                const size_t f = footprint(it, lens[i1]);
+                if (!take.empty() && bytes + f > budget) break;
+                bytes += f;
+                take.push_back(i1);
+            }
+            i1++;
+        }
+        i0 = i1;
+        if (take.empty()) break;
+        if (sl.cap < bytes) {
+            if (sl.mem) cudaFree(sl.mem);
+            sl.mem = nullptr; sl.cap = 0;
+            // (a first small batch reserves 1 GB so that the next ones need no new allocation)
+            size_t want = std::max(bytes, std::min(budget, (size_t)1 << 30));
+            if (cudaMalloc((void **)&sl.mem, want) != cudaSuccess) {
+                cudaGetLastError();
+                want = bytes;
+                if (cudaMalloc((void **)&sl.mem, want) != cudaSuccess) { cudaGetLastError(); sl.mem = nullptr; break; }   // the host path takes the rest
+            }
+            sl.cap = want;
+        }
+        size_t off = 0;
+        auto carve = [&](size_t nb) { uint8_t *p = sl.mem + off; off += al(nb); return p; };
+        // planes of the whole sub-batch first, contiguous: one memset
+        std::vector<zj::EntImage> eimg(take.size());
+        uint8_t *planes0 = sl.mem;
+        for (size_t t = 0; t < take.size(); t++) {
+            const Item &it = items[take[t]];
+            for (int z = 0; z < 3; z++) eimg[t].plane[z] = it.d->plane_len[z] ? (int16_t *)carve(it.d->plane_len[z] * 2) : nullptr;
+        }
+        const size_t plane_bytes = off;
+        lap("drain + cudaMalloc", nullptr);
+        bool ok = cudaMemsetAsync(planes0, 0, plane_bytes, sl.s) == cudaSuccess;
+        lap("memset planes", sl.s);
+        std::vector<zj::EntTable> tabs(6 * take.size());
+        std::vector<uint8_t *> pix(take.size());
+        sl.st_off.assign(take.size(), 0);
+        uint32_t max_seg = 0;
+        size_t st_total = 0;
+        for (size_t t = 0; t < take.size() && ok; t++) {
+            const size_t i = take[t];
+            Item &it = items[i];
+            zj::EntImage &e = eimg[t];
+            const zj_decoder::BaselineGeom &g = it.pp.g;
+            uint8_t *d_data = carve(lens[i] + 8);
+            ok = ok && cudaMemcpyAsync(d_data, bufs[i], lens[i], cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+            uint8_t *d_tab = carve(6 * sizeof(zj::EntTable));
+            it.d->gpu_entropy_tables(&tabs[6 * t]);
+            ok = ok && cudaMemcpyAsync(d_tab, &tabs[6 * t], 2 * g.ncomp * sizeof(zj::EntTable), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+            uint8_t *d_seg = carve((it.pp.n_seg + 1) * 4);
+            ok = ok && cudaMemcpyAsync(d_seg, it.pp.seg_start.data(), (it.pp.n_seg + 1) * 4, cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+            uint8_t *d_status = carve(it.pp.n_seg);
+            pix[t] = carve(it.need);
+            e.data = d_data; e.len = (uint32_t)lens[i];
+            e.seg_start = (const uint32_t *)d_seg; e.status = d_status; e.tables = (const zj::EntTable *)d_tab;
+            e.n_seg = (uint32_t)it.pp.n_seg; e.per_seg = (uint32_t)it.d->restart_interval; e.total_mcus = (uint32_t)it.pp.total;
+            e.restart_interval = (uint32_t)it.d->restart_interval;
+            e.mcu_w = (uint32_t)g.mcu_w; e.bias = (uint32_t)g.bias; e.ncomp = (uint32_t)g.ncomp; e.is_hv = g.is_hv ? 1u : 0u;
+            e.width_stride = (uint32_t)g.width_stride; e.hv_width_stride = (uint32_t)g.hv_width_stride;
+            for (int z = 0; z < 3; z++) {
+                e.strip_len[z] = (uint32_t)g.strip_len[z];
+                const bool have = (size_t)z < g.ncomp;
+                e.h_samp[z] = have ? (uint32_t)it.d->components[z].horizontal_sample : 0u;
+                e.v_samp[z] = have ? (uint32_t)it.d->components[z].vertical_sample : 0u;
+                e.is_y[z] = have && it.d->components[z].component_id == ID_Y ? 1u : 0u;
+            }
+            max_seg = std::max(max_seg, e.n_seg);
+            sl.st_off[t] = st_total;
+            st_total += it.pp.n_seg;
+        }
+        uint8_t *d_eimg = carve(eimg.size() * sizeof(zj::EntImage));
+        ok = ok && off <= sl.cap + 0 && cudaMemcpyAsync(d_eimg, eimg.data(), eimg.size() * sizeof(zj::EntImage), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+        lap("upload files + tables", sl.s);
+        ok = ok && zj::launch_entropy((const zj::EntImage *)d_eimg, (uint32_t)eimg.size(), max_seg, sl.s) == 0;
+        lap("entropy kernel", sl.s);
+        sl.st_host.assign(st_total, 1);
+        for (size_t t = 0; t < take.size() && ok; t++)
+            ok = cudaMemcpyAsync(sl.st_host.data() + sl.st_off[t], eimg[t].status, eimg[t].n_seg, cudaMemcpyDeviceToHost, sl.s) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(sl.s) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); which ^= 1; continue; }   // nothing published: these images go through the host path
+        // accepted images: reconstruct from the device planes, download
+        std::vector<zj_image> dimgs;
+        std::vector<uint8_t *> douts;
+        std::vector<size_t> dlens, who;
+        for (size_t t = 0; t < take.size(); t++) {
+            const size_t i = take[t];
+            Item &it = items[i];
+            bool all = true;
+            for (size_t k = 0; k < it.pp.n_seg; k++) all = all && sl.st_host[sl.st_off[t] + k] == 0;
+            if (!all) continue;
+            zj_image di = it.img;
+            for (uint32_t z = 0; z < di.n_comp; z++) di.comp[z].coeff = eimg[t].plane[z];
+            dimgs.push_back(di); douts.push_back(pix[t]); dlens.push_back(it.need); who.push_back(i);
+        }
+        if (!dimgs.empty()) {
+            int rc = zj_batch_create(opt.device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &sl.batch);
+            if (rc == ZJ_OK) rc = zj_batch_run(sl.batch, sl.s);
+            for (size_t t = 0; t < who.size() && rc == ZJ_OK; t++) {
+                const size_t i = who[t];
+                uint8_t *dst = out[i];
+                if (!dst) { dst = (uint8_t *)malloc(items[i].need); malloced[i] = dst; }
+                if (!dst) continue;
+                if (cudaMemcpyAsync(dst, douts[t], dlens[t], cudaMemcpyDeviceToHost, sl.s) != cudaSuccess) { cudaGetLastError(); continue; }
+                on_gpu[i] = 1;
+                sl.idx.push_back(i);
+            }
+            if (rc != ZJ_OK) rc_fatal = rc;
+        }
+        lap("status + reconstruct + d2h", trace ? sl.s : nullptr);
+        which ^= 1;
+    }
+    for (int k = 0; k < 2; k++) {
+        drain(slot[k]);
+        if (&sc == &own) {
+            if (slot[k].mem) cudaFree(slot[k].mem);
+            if (slot[k].s) cudaStreamDestroy(slot[k].s);
+        }
+    }
+    if (cache_lock.owns_lock()) cache_lock.unlock();
+    (void)rc_fatal;
+    size_t n_gpu = 0;
+    int failed = 0;
+    std::vector<size_t> rest;
+    for (size_t i = 0; i < n; i++) {
+        if (items[i].d) { zj_decoder_free(items[i].d); items[i].d = nullptr; }
+        if (on_gpu[i] == 2) {
+            n_gpu++;
+            status[i] = ZJ_OK;
+            if (malloced[i]) out[i] = malloced[i];
+            out_len[i] = items[i].need;
+        } else {
+            if (malloced[i]) { free(malloced[i]); malloced[i] = nullptr; }
+            rest.push_back(i);
+        }
+    }
+    if (n_gpu_entropy) *n_gpu_entropy = n_gpu;
+    // ---- everything else: the host stage
+    if (!rest.empty()) {
+        std::vector<const uint8_t *> b2(rest.size());
+        std::vector<size_t> l2(rest.size()), ol2(rest.size());
+        std::vector<uint8_t *> o2(rest.size());
+        std::vector<int> s2(rest.size(), 0);
+        for (size_t t = 0; t < rest.size(); t++) { b2[t] = bufs[rest[t]]; l2[t] = lens[rest[t]]; o2[t] = out[rest[t]]; ol2[t] = out_len[rest[t]]; }
+        const int f = zj_decode_batch(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data());
+        if (f < 0) return f;
+        failed += f;
+        for (size_t t = 0; t < rest.size(); t++) { out[rest[t]] = o2[t]; out_len[rest[t]] = ol2[t]; status[rest[t]] = s2[t]; }
+    }
+    return failed;
+}
+
 ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d) { return d ? d->last_entropy_segments : 0; }
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d) { return d ? d->err_kind : ZJ_DE_NONE; }
 ZJ_API const char *zj_decoder_error(const zj_decoder *d) { return d ? d->err_display.c_str() : ""; }

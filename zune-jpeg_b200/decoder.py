@@ -280,9 +280,11 @@ DecoderOptions = ZuneJpegOptions
 UnsupportedSchemes = enum.Enum("UnsupportedSchemes", "ExtendedSequentialHuffman LosslessHuffman ExtendedSequentialDctArithmetic ProgressiveDctArithmetic LosslessArithmetic")
 
 
-def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None):
+def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None, gpu_entropy: bool = False, stats: dict | None = None):
     """zj_decode_batch: JPEG byte strings in, pixel bytes out, `threads` host threads (0 = one per hardware thread)
     running the host stage of different images side by side while the GPU reconstructs the finished ones.
+    `gpu_entropy=True` (zj_decode_batch_gpu): baseline JPEGs with restart markers are entropy-decoded on the GPU as well, one
+    restart interval per thread; same results, `stats["gpu_entropy"]` = how many images took that route.
 
     Returns a list with one entry per input: `bytes` (or, with `out`, the number of bytes written into out[i]) for a decoded
     image, a `DecodeErrors` instance for a failed one.  `out`: optional list of writable buffers (e.g. PinnedBuffer.array
@@ -304,7 +306,13 @@ def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int =
         for i, v in enumerate(views):
             outs[i] = v.ctypes.data
             out_len[i] = v.nbytes
-    rc = lib.zj_decode_batch(C.byref(raw), bufs, lens, n, outs, out_len, status)
+    if gpu_entropy:
+        n_gpu = C.c_size_t(0)
+        rc = lib.zj_decode_batch_gpu(C.byref(raw), bufs, lens, n, outs, out_len, status, C.byref(n_gpu))
+        if stats is not None:
+            stats["gpu_entropy"] = int(n_gpu.value)
+    else:
+        rc = lib.zj_decode_batch(C.byref(raw), bufs, lens, n, outs, out_len, status)
     if rc < 0:
         raise DecodeErrors(13, lib.zj_gpu_strerror(rc).decode(), rc)
     res = []
