@@ -248,6 +248,11 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
  * errors are those of zj_decode_batch.  *n_gpu_entropy (may be NULL) = images whose entropy stage ran on the GPU. */
 ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                                uint8_t **out, size_t *out_len, int *status, size_t *n_gpu_entropy);
+/* ... and with the pixels left in device memory (no PCIe download at all: what is uploaded is the JPEG file): out_dev[i] is a
+ * device buffer of out_len[i] >= width*height*components bytes (sizes: zj_decoder_read_headers + zj_decoder_info); images
+ * that take the host route are uploaded after decoding.  The call returns when all pixels are in place. */
+ZJ_API int zj_decode_batch_gpu_device(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                                      uint8_t *const *out_dev, size_t *out_len, int *status, size_t *n_gpu_entropy);
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d);                 /* zj_decode_error_kind                */
 ZJ_API const char *zj_decoder_error(const zj_decoder *d);              /* Display text of the DecodeErrors    */
 

@@ -362,3 +362,29 @@ def test_gpu_entropy_decode_matches_host_stage():
         sure = sum(1 for c in cases if c[1] is True)
         maybe = sum(1 for c in cases if c[1] is None)
         assert sure <= stats["gpu_entropy"] <= sure + maybe, stats
+
+
+def test_gpu_entropy_decode_device_outputs():
+    """zj_decode_batch_gpu_device: pixels stay in device memory; GPU-entropy images and host-route images (no DRI) both land
+    there with the bytes Decoder.decode_buffer returns; a too small device buffer is a per-image error."""
+    import jpeg_util
+    from zune_jpeg_b200 import gpu
+    from zune_jpeg_b200.decoder import DecodeErrors, Decoder, decode_batch
+    jpegs = [jpeg_util.synth_jpeg(50, 1024, 768, "420", 90, restart_rows=1), jpeg_util.synth_jpeg(51, 800, 608, "420", 90),
+             jpeg_util.synth_jpeg(52, 1280, 720, "422", 85, restart_rows=2), jpeg_util.synth_jpeg(53, 640, 480, "444", 90, gray=True, restart_rows=1)]
+    wants = [Decoder.new().decode_buffer(j) for j in jpegs]
+    pinned_in = gpu.PinnedBuffer(sum(len(j) for j in jpegs))
+    ins, off = [], 0
+    for j in jpegs:
+        pinned_in.array[off:off + len(j)] = np.frombuffer(j, np.uint8)
+        ins.append(pinned_in.array[off:off + len(j)])
+        off += len(j)
+    bufs = [gpu.DeviceBuffer(len(w_) + 64) for w_ in wants]
+    stats = {}
+    res = decode_batch(ins, threads=4, device_out=[(b.ptr, b.nbytes) for b in bufs], stats=stats)
+    assert stats["gpu_entropy"] == 3
+    for r, w_, b in zip(res, wants, bufs):
+        assert r == len(w_)
+        assert b.download(len(w_)).tobytes() == w_
+    res = decode_batch(ins, threads=4, device_out=[(b.ptr, 1000) for b in bufs])
+    assert all(isinstance(r, DecodeErrors) for r in res)

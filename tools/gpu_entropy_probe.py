@@ -31,3 +31,19 @@ t0 = time.perf_counter()
 decode_batch(jpegs, o, threads=0, out=outs)
 dt = time.perf_counter() - t0
 print(f"host stage route: {1e3 * dt:.1f} ms, {n * w * h / 1e6 / dt:.0f} MP/s")
+# pixels left on the device, JPEG bytes from pinned memory
+import numpy as np  # noqa: E402
+pin = gpu.PinnedBuffer(sum(len(j) for j in jpegs))
+ins, off = [], 0
+for j in jpegs:
+    pin.array[off:off + len(j)] = np.frombuffer(j, np.uint8)
+    ins.append(pin.array[off:off + len(j)])
+    off += len(j)
+dev = [gpu.DeviceBuffer(out_bytes) for _ in range(min(n, 64))]
+targets = [(dev[i % len(dev)].ptr, out_bytes) for i in range(n)]
+for rep in range(3):
+    stats = {}
+    t0 = time.perf_counter()
+    decode_batch(ins, o, threads=0, device_out=targets, stats=stats)
+    dt = time.perf_counter() - t0
+    print(f"device out rep {rep}: {1e3 * dt:.1f} ms, {n * w * h / 1e6 / dt:.0f} MP/s, on GPU: {stats}", flush=True)

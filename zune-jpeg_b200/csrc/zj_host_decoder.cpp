@@ -1519,8 +1519,8 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
 // GPU thread into device planes, reconstructed in place and downloaded.  Every other image -- no DRI, progressive, a header
 // error, one interval that ends differently -- goes through zj_decode_batch (host stage), so results and errors are the
 // same as there.
-ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
-                               uint8_t **out, size_t *out_len, int *status, size_t *n_gpu_entropy)
+static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                                 uint8_t **out, size_t *out_len, int *status, size_t *n_gpu_entropy, const bool dev_out)
 {
     if (n_gpu_entropy) *n_gpu_entropy = 0;
     if ((!bufs || !lens || !out || !out_len || !status) && n) return ZJ_ERR_INVALID_ARG;
@@ -1529,7 +1529,10 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
     size_t nthreads = opt.num_threads ? opt.num_threads : std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 1;
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= opt.device) { cudaGetLastError(); return zj_decode_batch(o, bufs, lens, n, out, out_len, status); }
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= opt.device) {
+        cudaGetLastError();
+        return dev_out ? (int)ZJ_ERR_NO_DEVICE : zj_decode_batch(o, bufs, lens, n, out, out_len, status);
+    }
 
     const bool trace = getenv("ZJ_GPU_ENTROPY_TRACE") != nullptr;   // phase times on stderr (adds synchronisation)
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1560,7 +1563,7 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
                     if (it.gpu) {
                         it.d->fill_descriptor(&it.img);
                         it.need = zj_output_size(&it.img);
-                        if (it.need == 0 || (out[i] && out_len[i] < it.need)) it.gpu = false;   // the host path reports it
+                        if (it.need == 0 || (out[i] && out_len[i] < it.need) || (dev_out && !out[i])) it.gpu = false;   // the host path reports it
                         for (uint32_t z = 0; z < it.img.n_comp; z++) it.img.comp[z].coeff = it.img.comp[z].n_i16 ? (const int16_t *)16 : nullptr;
                         if (it.gpu && zj_validate_image(&it.img) != ZJ_OK) it.gpu = false;
                     }
@@ -1574,11 +1577,13 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
     }
 
     lap("headers + marker scan", nullptr);
-    // ---- GPU: sub-batches of as many images as fit the staging budget, two slots in flight
+    // ---- GPU: sub-batches of as many images as fit the staging budget, two slots in flight.  Stage 1 of sub-batch b (upload,
+    // clear the planes, entropy kernel, status download) is queued before the host waits for the statuses of sub-batch b-1 and
+    // queues its stage 2 (reconstruction, pixel download), so the two streams keep the GPU and both PCIe directions busy.
     std::vector<char> on_gpu(n, 0);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     auto footprint = [&](const Item &it, size_t len) {
-        size_t b = al(len + 8) + al(sizeof(zj::EntImage)) + al(6 * sizeof(zj::EntTable)) + al((it.pp.n_seg + 1) * 4) + al(it.pp.n_seg) + al(it.need);
+        size_t b = al(len + 8) + al(sizeof(zj::EntImage)) + al(6 * sizeof(zj::EntTable)) + al((it.pp.n_seg + 1) * 4) + al(it.pp.n_seg) + (dev_out ? 0 : al(it.need));
         for (int z = 0; z < 3; z++) b += al(it.d->plane_len[z] * 2);
         return b;
     };
@@ -1586,8 +1591,13 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
     const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : 4096) << 20;
     struct Slot {
         cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
-        std::vector<size_t> idx; zj_batch *batch = nullptr;
+        zj_batch *batch = nullptr;
+        std::vector<size_t> take, idx;            // images of the sub-batch in stage 1 / images whose pixels are on their way
+        std::vector<zj::EntImage> eimg;
+        std::vector<zj::EntTable> tabs;
+        std::vector<uint8_t *> pix;
         std::vector<uint8_t> st_host; std::vector<size_t> st_off;
+        bool staged = false;
     };
     // the two slots' streams and device memory are kept between calls (allocating and freeing gigabytes costs 3-13 ms per
     // call and synchronises the device); one call at a time uses them, a concurrent call works with slots of its own
@@ -1607,37 +1617,35 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
         sc.device = opt.device;
     }
     Slot *slot = sc.slot;
-    int rc_fatal = ZJ_OK;
     for (int k = 0; k < 2 && cuda_ok; k++)
         if (!slot[k].s) cuda_ok = cudaStreamCreateWithFlags(&slot[k].s, cudaStreamNonBlocking) == cudaSuccess;
+    std::vector<uint8_t *> malloced(n, nullptr);
     auto drain = [&](Slot &sl) {   // wait for the slot's downloads, publish its images
-        if (sl.idx.empty()) return;
+        if (sl.idx.empty() && !sl.batch) return;
         const bool ok = cudaStreamSynchronize(sl.s) == cudaSuccess;
+        if (!ok) cudaGetLastError();
         if (sl.batch) { zj_batch_destroy(sl.batch); sl.batch = nullptr; }
         for (size_t i : sl.idx) if (on_gpu[i] == 1) on_gpu[i] = ok ? 2 : 0;
         sl.idx.clear();
     };
-    std::vector<uint8_t *> malloced(n, nullptr);
     size_t i0 = 0;
-    int which = 0;
-    while (cuda_ok && i0 < n) {
-        // next run of images for this slot
-        Slot &sl = slot[which];
-        drain(sl);
+    // stage 1: false when there is nothing (left) to queue
+    auto stage1 = [&](Slot &sl) -> bool {
+        sl.staged = false;
+        sl.take.clear();
         size_t bytes = 0, i1 = i0;
-        std::vector<size_t> take;
         while (i1 < n) {
             const Item &it = items[i1];
             if (it.gpu) {
                 const size_t f = footprint(it, lens[i1]);
-                if (!take.empty() && bytes + f > budget) break;
+                if (!sl.take.empty() && bytes + f > budget) break;
                 bytes += f;
-                take.push_back(i1);
+                sl.take.push_back(i1);
             }
             i1++;
         }
         i0 = i1;
-        if (take.empty()) break;
+        if (sl.take.empty()) return false;
         if (sl.cap < bytes) {
             if (sl.mem) cudaFree(sl.mem);
             sl.mem = nullptr; sl.cap = 0;
@@ -1646,42 +1654,41 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
             if (cudaMalloc((void **)&sl.mem, want) != cudaSuccess) {
                 cudaGetLastError();
                 want = bytes;
-                if (cudaMalloc((void **)&sl.mem, want) != cudaSuccess) { cudaGetLastError(); sl.mem = nullptr; break; }   // the host path takes the rest
+                if (cudaMalloc((void **)&sl.mem, want) != cudaSuccess) { cudaGetLastError(); sl.mem = nullptr; sl.take.clear(); return true; }   // host path
             }
             sl.cap = want;
         }
+        lap("take + cudaMalloc", nullptr);
+        const std::vector<size_t> &take = sl.take;
         size_t off = 0;
         auto carve = [&](size_t nb) { uint8_t *p = sl.mem + off; off += al(nb); return p; };
         // planes of the whole sub-batch first, contiguous: one memset
-        std::vector<zj::EntImage> eimg(take.size());
-        uint8_t *planes0 = sl.mem;
+        sl.eimg.assign(take.size(), zj::EntImage{});
         for (size_t t = 0; t < take.size(); t++) {
             const Item &it = items[take[t]];
-            for (int z = 0; z < 3; z++) eimg[t].plane[z] = it.d->plane_len[z] ? (int16_t *)carve(it.d->plane_len[z] * 2) : nullptr;
+            for (int z = 0; z < 3; z++) sl.eimg[t].plane[z] = it.d->plane_len[z] ? (int16_t *)carve(it.d->plane_len[z] * 2) : nullptr;
         }
-        const size_t plane_bytes = off;
-        lap("drain + cudaMalloc", nullptr);
-        bool ok = cudaMemsetAsync(planes0, 0, plane_bytes, sl.s) == cudaSuccess;
+        bool ok = cudaMemsetAsync(sl.mem, 0, off, sl.s) == cudaSuccess;
         lap("memset planes", sl.s);
-        std::vector<zj::EntTable> tabs(6 * take.size());
-        std::vector<uint8_t *> pix(take.size());
+        sl.tabs.resize(6 * take.size());
+        sl.pix.assign(take.size(), nullptr);
         sl.st_off.assign(take.size(), 0);
         uint32_t max_seg = 0;
         size_t st_total = 0;
         for (size_t t = 0; t < take.size() && ok; t++) {
             const size_t i = take[t];
             Item &it = items[i];
-            zj::EntImage &e = eimg[t];
+            zj::EntImage &e = sl.eimg[t];
             const zj_decoder::BaselineGeom &g = it.pp.g;
             uint8_t *d_data = carve(lens[i] + 8);
             ok = ok && cudaMemcpyAsync(d_data, bufs[i], lens[i], cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
             uint8_t *d_tab = carve(6 * sizeof(zj::EntTable));
-            it.d->gpu_entropy_tables(&tabs[6 * t]);
-            ok = ok && cudaMemcpyAsync(d_tab, &tabs[6 * t], 2 * g.ncomp * sizeof(zj::EntTable), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+            it.d->gpu_entropy_tables(&sl.tabs[6 * t]);
+            ok = ok && cudaMemcpyAsync(d_tab, &sl.tabs[6 * t], 2 * g.ncomp * sizeof(zj::EntTable), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
             uint8_t *d_seg = carve((it.pp.n_seg + 1) * 4);
             ok = ok && cudaMemcpyAsync(d_seg, it.pp.seg_start.data(), (it.pp.n_seg + 1) * 4, cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
             uint8_t *d_status = carve(it.pp.n_seg);
-            pix[t] = carve(it.need);
+            sl.pix[t] = dev_out ? out[i] : carve(it.need);
             e.data = d_data; e.len = (uint32_t)lens[i];
             e.seg_start = (const uint32_t *)d_seg; e.status = d_status; e.tables = (const zj::EntTable *)d_tab;
             e.n_seg = (uint32_t)it.pp.n_seg; e.per_seg = (uint32_t)it.d->restart_interval; e.total_mcus = (uint32_t)it.pp.total;
@@ -1699,56 +1706,74 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
             sl.st_off[t] = st_total;
             st_total += it.pp.n_seg;
         }
-        uint8_t *d_eimg = carve(eimg.size() * sizeof(zj::EntImage));
-        ok = ok && off <= sl.cap + 0 && cudaMemcpyAsync(d_eimg, eimg.data(), eimg.size() * sizeof(zj::EntImage), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+        uint8_t *d_eimg = carve(sl.eimg.size() * sizeof(zj::EntImage));
+        ok = ok && off <= sl.cap && cudaMemcpyAsync(d_eimg, sl.eimg.data(), sl.eimg.size() * sizeof(zj::EntImage), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
         lap("upload files + tables", sl.s);
-        ok = ok && zj::launch_entropy((const zj::EntImage *)d_eimg, (uint32_t)eimg.size(), max_seg, sl.s) == 0;
+        ok = ok && zj::launch_entropy((const zj::EntImage *)d_eimg, (uint32_t)sl.eimg.size(), max_seg, sl.s) == 0;
         lap("entropy kernel", sl.s);
         sl.st_host.assign(st_total, 1);
         for (size_t t = 0; t < take.size() && ok; t++)
-            ok = cudaMemcpyAsync(sl.st_host.data() + sl.st_off[t], eimg[t].status, eimg[t].n_seg, cudaMemcpyDeviceToHost, sl.s) == cudaSuccess;
-        ok = ok && cudaStreamSynchronize(sl.s) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); which ^= 1; continue; }   // nothing published: these images go through the host path
-        // accepted images: reconstruct from the device planes, download
+            ok = cudaMemcpyAsync(sl.st_host.data() + sl.st_off[t], sl.eimg[t].status, sl.eimg[t].n_seg, cudaMemcpyDeviceToHost, sl.s) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        sl.staged = ok;   // (not staged: nothing is published, these images go through the host path)
+        return true;
+    };
+    // stage 2: the statuses are in; accepted images are reconstructed from their device planes and downloaded
+    auto stage2 = [&](Slot &sl) {
+        if (!sl.staged) return;
+        sl.staged = false;
+        if (cudaStreamSynchronize(sl.s) != cudaSuccess) { cudaGetLastError(); return; }
         std::vector<zj_image> dimgs;
         std::vector<uint8_t *> douts;
         std::vector<size_t> dlens, who;
-        for (size_t t = 0; t < take.size(); t++) {
-            const size_t i = take[t];
+        for (size_t t = 0; t < sl.take.size(); t++) {
+            const size_t i = sl.take[t];
             Item &it = items[i];
             bool all = true;
             for (size_t k = 0; k < it.pp.n_seg; k++) all = all && sl.st_host[sl.st_off[t] + k] == 0;
             if (!all) continue;
             zj_image di = it.img;
-            for (uint32_t z = 0; z < di.n_comp; z++) di.comp[z].coeff = eimg[t].plane[z];
-            dimgs.push_back(di); douts.push_back(pix[t]); dlens.push_back(it.need); who.push_back(i);
+            for (uint32_t z = 0; z < di.n_comp; z++) di.comp[z].coeff = sl.eimg[t].plane[z];
+            dimgs.push_back(di); douts.push_back(sl.pix[t]); dlens.push_back(it.need); who.push_back(i);
         }
-        if (!dimgs.empty()) {
-            int rc = zj_batch_create(opt.device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &sl.batch);
-            if (rc == ZJ_OK) rc = zj_batch_run(sl.batch, sl.s);
-            for (size_t t = 0; t < who.size() && rc == ZJ_OK; t++) {
-                const size_t i = who[t];
+        if (dimgs.empty()) return;
+        int rc = zj_batch_create(opt.device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &sl.batch);
+        if (rc == ZJ_OK) rc = zj_batch_run(sl.batch, sl.s);
+        for (size_t t = 0; t < who.size() && rc == ZJ_OK; t++) {
+            const size_t i = who[t];
+            if (!dev_out) {
                 uint8_t *dst = out[i];
                 if (!dst) { dst = (uint8_t *)malloc(items[i].need); malloced[i] = dst; }
                 if (!dst) continue;
                 if (cudaMemcpyAsync(dst, douts[t], dlens[t], cudaMemcpyDeviceToHost, sl.s) != cudaSuccess) { cudaGetLastError(); continue; }
-                on_gpu[i] = 1;
-                sl.idx.push_back(i);
             }
-            if (rc != ZJ_OK) rc_fatal = rc;
+            on_gpu[i] = 1;
+            sl.idx.push_back(i);
         }
-        lap("status + reconstruct + d2h", trace ? sl.s : nullptr);
-        which ^= 1;
+        lap("status + reconstruct (+ d2h)", trace ? sl.s : nullptr);
+    };
+    if (cuda_ok) {
+        int cur = 0;
+        bool more = true;
+        while (more) {
+            Slot &sl = slot[cur];
+            drain(sl);
+            more = stage1(sl);
+            stage2(slot[cur ^ 1]);
+            cur ^= 1;
+        }
+        stage2(slot[0]);
+        stage2(slot[1]);
     }
     for (int k = 0; k < 2; k++) {
         drain(slot[k]);
+        slot[k].take.clear();
         if (&sc == &own) {
             if (slot[k].mem) cudaFree(slot[k].mem);
             if (slot[k].s) cudaStreamDestroy(slot[k].s);
         }
     }
     if (cache_lock.owns_lock()) cache_lock.unlock();
-    (void)rc_fatal;
     size_t n_gpu = 0;
     int failed = 0;
     std::vector<size_t> rest;
@@ -1771,13 +1796,41 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
         std::vector<size_t> l2(rest.size()), ol2(rest.size());
         std::vector<uint8_t *> o2(rest.size());
         std::vector<int> s2(rest.size(), 0);
-        for (size_t t = 0; t < rest.size(); t++) { b2[t] = bufs[rest[t]]; l2[t] = lens[rest[t]]; o2[t] = out[rest[t]]; ol2[t] = out_len[rest[t]]; }
-        const int f = zj_decode_batch(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data());
+        for (size_t t = 0; t < rest.size(); t++) {
+            b2[t] = bufs[rest[t]]; l2[t] = lens[rest[t]];
+            o2[t] = dev_out ? nullptr : out[rest[t]];          // device outputs: decoded into host memory first, then uploaded
+            ol2[t] = dev_out ? 0 : out_len[rest[t]];
+        }
+        int f = zj_decode_batch(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data());
         if (f < 0) return f;
+        for (size_t t = 0; t < rest.size(); t++) {
+            const size_t i = rest[t];
+            if (!dev_out) { out[i] = o2[t]; out_len[i] = ol2[t]; status[i] = s2[t]; continue; }
+            int rc = s2[t];
+            if (rc == ZJ_OK) {
+                if (!out[i]) rc = ZJ_ERR_INVALID_ARG;
+                else if (out_len[i] < ol2[t]) rc = ZJ_ERR_SHORT_OUTPUT;
+                else if (cudaMemcpy(out[i], o2[t], ol2[t], cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); rc = ZJ_ERR_CUDA; }
+                if (rc != ZJ_OK) f++;
+            }
+            free(o2[t]);
+            out_len[i] = rc == ZJ_OK ? ol2[t] : 0;
+            status[i] = rc;
+        }
         failed += f;
-        for (size_t t = 0; t < rest.size(); t++) { out[rest[t]] = o2[t]; out_len[rest[t]] = ol2[t]; status[rest[t]] = s2[t]; }
     }
     return failed;
+}
+
+ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                               uint8_t **out, size_t *out_len, int *status, size_t *n_gpu_entropy)
+{
+    return decode_batch_gpu_impl(o, bufs, lens, n, out, out_len, status, n_gpu_entropy, false);
+}
+ZJ_API int zj_decode_batch_gpu_device(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                                      uint8_t *const *out_dev, size_t *out_len, int *status, size_t *n_gpu_entropy)
+{
+    return decode_batch_gpu_impl(o, bufs, lens, n, const_cast<uint8_t **>(out_dev), out_len, status, n_gpu_entropy, true);
 }
 
 ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d) { return d ? d->last_entropy_segments : 0; }

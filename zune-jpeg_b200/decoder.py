@@ -280,35 +280,43 @@ DecoderOptions = ZuneJpegOptions
 UnsupportedSchemes = enum.Enum("UnsupportedSchemes", "ExtendedSequentialHuffman LosslessHuffman ExtendedSequentialDctArithmetic ProgressiveDctArithmetic LosslessArithmetic")
 
 
-def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None, gpu_entropy: bool = False, stats: dict | None = None):
+def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None, gpu_entropy: bool = False, stats: dict | None = None,
+                 device_out=None):
     """zj_decode_batch: JPEG byte strings in, pixel bytes out, `threads` host threads (0 = one per hardware thread)
     running the host stage of different images side by side while the GPU reconstructs the finished ones.
     `gpu_entropy=True` (zj_decode_batch_gpu): baseline JPEGs with restart markers are entropy-decoded on the GPU as well, one
     restart interval per thread; same results, `stats["gpu_entropy"]` = how many images took that route.
+    `device_out=[(device_ptr, nbytes), ...]` (zj_decode_batch_gpu_device): the pixels stay in device memory.
 
-    Returns a list with one entry per input: `bytes` (or, with `out`, the number of bytes written into out[i]) for a decoded
+    Returns a list with one entry per input: `bytes` (or, with `out` / `device_out`, the number of bytes written) for a decoded
     image, a `DecodeErrors` instance for a failed one.  `out`: optional list of writable buffers (e.g. PinnedBuffer.array
-    slices), one per image, large enough for width*height*components."""
+    slices), one per image, large enough for width*height*components.  Inputs may be `bytes` or uint8 numpy arrays (e.g. views
+    of pinned memory, which upload at the full PCIe rate)."""
     import numpy as np
     lib = _ffi.load()
     options = options if options is not None else ZuneJpegOptions()
     raw = options._raw()
     raw.num_threads = int(threads)
     n = len(buffers)
-    keep = [bytes(b) for b in buffers]
-    bufs = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p).value for b in keep])
-    lens = (C.c_size_t * n)(*[len(b) for b in keep])
+    keep = [b if isinstance(b, np.ndarray) else bytes(b) for b in buffers]
+    bufs = (C.c_void_p * n)(*[b.ctypes.data if isinstance(b, np.ndarray) else C.cast(C.c_char_p(b), C.c_void_p).value for b in keep])
+    lens = (C.c_size_t * n)(*[b.nbytes if isinstance(b, np.ndarray) else len(b) for b in keep])
     outs = (C.c_void_p * n)()
     out_len = (C.c_size_t * n)()
     status = (C.c_int * n)()
-    if out is not None:
+    if device_out is not None:
+        for i, (ptr, nbytes) in enumerate(device_out):
+            outs[i] = ptr
+            out_len[i] = nbytes
+    elif out is not None:
         views = [np.frombuffer(o, dtype=np.uint8) if not isinstance(o, np.ndarray) else o for o in out]
         for i, v in enumerate(views):
             outs[i] = v.ctypes.data
             out_len[i] = v.nbytes
-    if gpu_entropy:
+    if gpu_entropy or device_out is not None:
         n_gpu = C.c_size_t(0)
-        rc = lib.zj_decode_batch_gpu(C.byref(raw), bufs, lens, n, outs, out_len, status, C.byref(n_gpu))
+        fn = lib.zj_decode_batch_gpu_device if device_out is not None else lib.zj_decode_batch_gpu
+        rc = fn(C.byref(raw), bufs, lens, n, outs, out_len, status, C.byref(n_gpu))
         if stats is not None:
             stats["gpu_entropy"] = int(n_gpu.value)
     else:
@@ -319,7 +327,7 @@ def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int =
     for i in range(n):
         if status[i] != 0:
             res.append(DecodeErrors(13 if status[i] != _ffi.ERR_DECODE else 1, lib.zj_gpu_strerror(status[i]).decode(), status[i]))
-        elif out is not None:
+        elif out is not None or device_out is not None:
             res.append(int(out_len[i]))
         else:
             try:
@@ -327,4 +335,3 @@ def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int =
             finally:
                 lib.zj_buffer_free(outs[i])
     return res
-
