@@ -1583,21 +1583,31 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     std::vector<char> on_gpu(n, 0);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     auto footprint = [&](const Item &it, size_t len) {
-        size_t b = al(len + 8) + al(sizeof(zj::EntImage)) + al(6 * sizeof(zj::EntTable)) + al((it.pp.n_seg + 1) * 4) + al(it.pp.n_seg) + (dev_out ? 0 : al(it.need));
+        size_t b = al(len + 8) + al(sizeof(zj::EntImage)) + al(6 * sizeof(zj::EntTable)) + al((it.pp.n_seg + 1) * 4) + al(it.pp.n_seg) + 1024 + (dev_out ? 0 : al(it.need));
         for (int z = 0; z < 3; z++) b += al(it.d->plane_len[z] * 2);
         return b;
     };
     const char *env_mb = getenv("ZJ_GPU_ENTROPY_BUDGET_MB");
-    const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : 4096) << 20;
+    const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : 8192) << 20;
     struct Slot {
         cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
         zj_batch *batch = nullptr;
         std::vector<size_t> take, idx;            // images of the sub-batch in stage 1 / images whose pixels are on their way
         std::vector<zj::EntImage> eimg;
-        std::vector<zj::EntTable> tabs;
         std::vector<uint8_t *> pix;
-        std::vector<uint8_t> st_host; std::vector<size_t> st_off;
+        std::vector<size_t> st_off;
+        uint8_t *meta_host = nullptr, *st_host = nullptr;   // pinned: descriptors + tables + interval starts up, statuses down
+        size_t meta_cap = 0, st_cap = 0;
         bool staged = false;
+    };
+    auto pinned_grow = [](uint8_t *&p, size_t &cap, size_t need) -> bool {
+        if (cap >= need) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = need + need / 2 + 4096;
+        if (cudaHostAlloc((void **)&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+        cap = want;
+        return true;
     };
     // the two slots' streams and device memory are kept between calls (allocating and freeing gigabytes costs 3-13 ms per
     // call and synchronises the device); one call at a time uses them, a concurrent call works with slots of its own
@@ -1612,6 +1622,8 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         for (auto &sl : sc.slot) {
             if (sl.mem) cudaFree(sl.mem);
             if (sl.s) cudaStreamDestroy(sl.s);
+            if (sl.meta_host) cudaFreeHost(sl.meta_host);
+            if (sl.st_host) cudaFreeHost(sl.st_host);
             sl = Slot{};
         }
         sc.device = opt.device;
@@ -1670,11 +1682,17 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         }
         bool ok = cudaMemsetAsync(sl.mem, 0, off, sl.s) == cudaSuccess;
         lap("memset planes", sl.s);
-        sl.tabs.resize(6 * take.size());
+        // descriptors, Huffman tables and interval starts of the sub-batch travel as ONE pinned block, the statuses come back as one
         sl.pix.assign(take.size(), nullptr);
         sl.st_off.assign(take.size(), 0);
+        size_t st_total = 0, seg_words = 0;
+        for (size_t t = 0; t < take.size(); t++) { sl.st_off[t] = st_total; st_total += items[take[t]].pp.n_seg; seg_words += items[take[t]].pp.n_seg + 1; }
+        const size_t off_tab = al(take.size() * sizeof(zj::EntImage)), off_seg = off_tab + al(6 * take.size() * sizeof(zj::EntTable));
+        const size_t meta_bytes = off_seg + al(seg_words * 4);
+        ok = ok && pinned_grow(sl.meta_host, sl.meta_cap, meta_bytes) && pinned_grow(sl.st_host, sl.st_cap, st_total);
+        uint8_t *d_meta = carve(meta_bytes), *d_status = carve(st_total);
         uint32_t max_seg = 0;
-        size_t st_total = 0;
+        size_t seg_at = 0;
         for (size_t t = 0; t < take.size() && ok; t++) {
             const size_t i = take[t];
             Item &it = items[i];
@@ -1682,15 +1700,14 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
             const zj_decoder::BaselineGeom &g = it.pp.g;
             uint8_t *d_data = carve(lens[i] + 8);
             ok = ok && cudaMemcpyAsync(d_data, bufs[i], lens[i], cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
-            uint8_t *d_tab = carve(6 * sizeof(zj::EntTable));
-            it.d->gpu_entropy_tables(&sl.tabs[6 * t]);
-            ok = ok && cudaMemcpyAsync(d_tab, &sl.tabs[6 * t], 2 * g.ncomp * sizeof(zj::EntTable), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
-            uint8_t *d_seg = carve((it.pp.n_seg + 1) * 4);
-            ok = ok && cudaMemcpyAsync(d_seg, it.pp.seg_start.data(), (it.pp.n_seg + 1) * 4, cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
-            uint8_t *d_status = carve(it.pp.n_seg);
+            it.d->gpu_entropy_tables(reinterpret_cast<zj::EntTable *>(sl.meta_host + off_tab) + 6 * t);
+            memcpy(sl.meta_host + off_seg + seg_at * 4, it.pp.seg_start.data(), (it.pp.n_seg + 1) * 4);
             sl.pix[t] = dev_out ? out[i] : carve(it.need);
             e.data = d_data; e.len = (uint32_t)lens[i];
-            e.seg_start = (const uint32_t *)d_seg; e.status = d_status; e.tables = (const zj::EntTable *)d_tab;
+            e.seg_start = reinterpret_cast<const uint32_t *>(d_meta + off_seg) + seg_at;
+            e.status = d_status + sl.st_off[t];
+            e.tables = reinterpret_cast<const zj::EntTable *>(d_meta + off_tab) + 6 * t;
+            seg_at += it.pp.n_seg + 1;
             e.n_seg = (uint32_t)it.pp.n_seg; e.per_seg = (uint32_t)it.d->restart_interval; e.total_mcus = (uint32_t)it.pp.total;
             e.restart_interval = (uint32_t)it.d->restart_interval;
             e.mcu_w = (uint32_t)g.mcu_w; e.bias = (uint32_t)g.bias; e.ncomp = (uint32_t)g.ncomp; e.is_hv = g.is_hv ? 1u : 0u;
@@ -1703,17 +1720,13 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
                 e.is_y[z] = have && it.d->components[z].component_id == ID_Y ? 1u : 0u;
             }
             max_seg = std::max(max_seg, e.n_seg);
-            sl.st_off[t] = st_total;
-            st_total += it.pp.n_seg;
         }
-        uint8_t *d_eimg = carve(sl.eimg.size() * sizeof(zj::EntImage));
-        ok = ok && off <= sl.cap && cudaMemcpyAsync(d_eimg, sl.eimg.data(), sl.eimg.size() * sizeof(zj::EntImage), cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
+        if (ok) memcpy(sl.meta_host, sl.eimg.data(), take.size() * sizeof(zj::EntImage));
+        ok = ok && off <= sl.cap && cudaMemcpyAsync(d_meta, sl.meta_host, meta_bytes, cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
         lap("upload files + tables", sl.s);
-        ok = ok && zj::launch_entropy((const zj::EntImage *)d_eimg, (uint32_t)sl.eimg.size(), max_seg, sl.s) == 0;
+        ok = ok && zj::launch_entropy(reinterpret_cast<const zj::EntImage *>(d_meta), (uint32_t)take.size(), max_seg, sl.s) == 0;
         lap("entropy kernel", sl.s);
-        sl.st_host.assign(st_total, 1);
-        for (size_t t = 0; t < take.size() && ok; t++)
-            ok = cudaMemcpyAsync(sl.st_host.data() + sl.st_off[t], sl.eimg[t].status, sl.eimg[t].n_seg, cudaMemcpyDeviceToHost, sl.s) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(sl.st_host, d_status, st_total, cudaMemcpyDeviceToHost, sl.s) == cudaSuccess;
         if (!ok) cudaGetLastError();
         sl.staged = ok;   // (not staged: nothing is published, these images go through the host path)
         return true;
@@ -1771,6 +1784,8 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         if (&sc == &own) {
             if (slot[k].mem) cudaFree(slot[k].mem);
             if (slot[k].s) cudaStreamDestroy(slot[k].s);
+            if (slot[k].meta_host) cudaFreeHost(slot[k].meta_host);
+            if (slot[k].st_host) cudaFreeHost(slot[k].st_host);
         }
     }
     if (cache_lock.owns_lock()) cache_lock.unlock();
