@@ -1588,7 +1588,7 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         return b;
     };
     const char *env_mb = getenv("ZJ_GPU_ENTROPY_BUDGET_MB");
-    const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : 8192) << 20;
+    const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : (dev_out ? 8192 : 2048)) << 20;   // host outputs: smaller sub-batches, so that the download of one overlaps the kernels of the next
     struct Slot {
         cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
         zj_batch *batch = nullptr;
