@@ -388,3 +388,48 @@ def test_gpu_entropy_decode_device_outputs():
         assert b.download(len(w_)).tobytes() == w_
     res = decode_batch(ins, threads=4, device_out=[(b.ptr, 1000) for b in bufs])
     assert all(isinstance(r, DecodeErrors) for r in res)
+
+
+def test_gpu_entropy_decode_fuzz():
+    """Damaged restart-marker streams, many at once: whatever route an image ends up on (GPU intervals accepted, or the host
+    stage after a rejected interval), pixels and per-image errors equal those of the host stage alone."""
+    import jpeg_util
+    from zune_jpeg_b200.decoder import DecodeErrors, decode_batch
+    rng = np.random.default_rng(77)
+    bases = [jpeg_util.synth_jpeg(60, 640, 480, "420", 85, restart_rows=1), jpeg_util.synth_jpeg(61, 512, 384, "444", 92, restart_rows=2),
+             jpeg_util.synth_jpeg(62, 768, 256, "422", 70, restart_rows=1), jpeg_util.synth_jpeg(63, 512, 512, "444", 90, gray=True, restart_rows=1)]
+    jpegs = []
+    for k in range(64):
+        d = bytearray(bases[k % len(bases)])
+        sos = bytes(d).index(b"\xff\xda")
+        kind = k % 6
+        if kind == 0:      # bit flips in the entropy-coded data
+            for p in rng.integers(sos + 14, len(d) - 2, size=int(rng.integers(1, 5))):
+                d[p] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:    # truncation
+            del d[int(rng.integers(sos + 14, len(d) - 2)):]
+        elif kind == 2:    # a restart marker removed / duplicated
+            marks = [i for i in range(sos, len(d) - 1) if d[i] == 0xFF and 0xD0 <= d[i + 1] <= 0xD7]
+            p = marks[int(rng.integers(0, len(marks)))]
+            if k % 12 < 6:
+                del d[p:p + 2]
+            else:
+                d[p:p] = d[p:p + 2]
+        elif kind == 3:    # a foreign marker / stuffed 0xFF bytes inside the scan
+            p = int(rng.integers(sos + 14, len(d) - 2))
+            d[p:p] = [b"\xff\xd9", b"\xff\xc4", b"\xff\xff\xff\x00", b"\xff\x01"][k // 6 % 4]
+        elif kind == 4:    # DRI changed
+            i = bytes(d).index(b"\xff\xdd")
+            v = int(rng.integers(1, 400))
+            d[i + 4:i + 6] = bytes([v >> 8, v & 255])
+        # kind 5: untouched
+        jpegs.append(bytes(d))
+    want = decode_batch(jpegs, threads=4)
+    stats = {}
+    got = decode_batch(jpegs, threads=4, gpu_entropy=True, stats=stats)
+    assert stats["gpu_entropy"] >= 64 // 6
+    for k, (g, w_) in enumerate(zip(got, want)):
+        if isinstance(w_, DecodeErrors):
+            assert isinstance(g, DecodeErrors) and g.status == w_.status, k
+        else:
+            assert g == w_, f"image {k} (kind {k % 6})"
