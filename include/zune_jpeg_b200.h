@@ -240,6 +240,9 @@ ZJ_API void zj_buffer_free(uint8_t *p);
  * images (0 = all decoded) or a negative zj_status for invalid arguments. */
 ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                            uint8_t **out, size_t *out_len, int *status);
+/* zj_decode_batch keeps its workers' decoders (pinned coefficient planes sized for the largest image seen, two per host
+ * thread) for the next call; this frees them. */
+ZJ_API void zj_release_host_caches(void);
 /* The same call with the entropy stage on the GPU too, for the JPEGs that allow it: baseline scans with restart markers (DRI)
  * whose every interval ends the way the reference's sequential loop (src/mcu.rs:253-351, 386-418) ends it.  Their files are
  * uploaded instead of their coefficient planes, one GPU thread per restart interval runs the reference's bit reader and MCU

@@ -286,6 +286,10 @@ def test_decode_batch_matches_single_image_decodes():
     assert res == sizes
     for j, o in zip(jpegs, outs):
         assert o.tobytes() == Decoder.new_with_options(opts).decode_buffer(j)
+    # the workers' pooled decoders can be dropped between calls
+    from zune_jpeg_b200 import _ffi
+    _ffi.load().zj_release_host_caches()
+    assert decode_batch(jpegs[:3], threads=2) == wants[:3]
 
 
 @pytest.mark.parametrize("w,h,mode", [(2500, 1786, "444"), (2500, 1786, "422"), (2500, 1786, "440"), (3024, 4032, "420"),

@@ -118,6 +118,7 @@ SYMBOLS = {
                                       C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "zj_decode_batch_gpu_device": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
                                              C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "zj_release_host_caches": (None, []),
     "zj_decoder_entropy_segments": (C.c_size_t, [_P]),
     "zj_decoder_error_kind": (C.c_int, [_P]),
     "zj_decoder_error": (C.c_char_p, [_P]),

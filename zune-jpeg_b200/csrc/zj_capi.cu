@@ -443,7 +443,30 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         uint8_t *buf[64][NS_MAX] = {};
         size_t cap[64][NS_MAX] = {};
     };
-    thread_local StreamCache cache;
+    // A thread leases a cache for its lifetime and hands it back when it exits (zj_decode_batch starts fresh worker threads
+    // in every call: a plain thread_local would strand its streams and device buffers with every one of them).
+    struct CachePool {
+        std::mutex mu;
+        std::vector<StreamCache *> idle;
+    };
+    static CachePool pool;
+    struct Lease {
+        StreamCache *c = nullptr;
+        ~Lease()
+        {
+            if (!c) return;
+            std::lock_guard<std::mutex> lock(pool.mu);
+            pool.idle.push_back(c);
+        }
+    };
+    thread_local Lease lease;
+    if (!lease.c) {
+        std::lock_guard<std::mutex> lock(pool.mu);
+        if (!pool.idle.empty()) { lease.c = pool.idle.back(); pool.idle.pop_back(); }
+    }
+    if (!lease.c) lease.c = new (std::nothrow) StreamCache;
+    if (!lease.c) return ZJ_ERR_OOM;
+    StreamCache &cache = *lease.c;
     if (device >= 64) return ZJ_ERR_NO_DEVICE;
     for (int k = 0; k < NS; k++) {
         if (!cache.s[device][k]) CU(cudaStreamCreateWithFlags(&cache.s[device][k], cudaStreamNonBlocking));

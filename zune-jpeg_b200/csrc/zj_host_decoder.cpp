@@ -1415,6 +1415,19 @@ ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t le
 }
 ZJ_API void zj_buffer_free(uint8_t *p) { free(p); }
 
+// decoders (with their pinned coefficient planes) kept between zj_decode_batch calls; zj_release_host_caches frees them
+static std::mutex g_idle_mu;
+static std::vector<zj_decoder *> g_idle;
+ZJ_API void zj_release_host_caches(void)
+{
+    std::vector<zj_decoder *> drop;
+    {
+        std::lock_guard<std::mutex> lock(g_idle_mu);
+        drop.swap(g_idle);
+    }
+    for (zj_decoder *d : drop) zj_decoder_free(d);
+}
+
 // Batch front door.  The reference decodes one image per Decoder and parallelises the strips of that image
 // (scoped_threadpool, mcu.rs:230-369); with the pixel path on the GPU the host threads are free to run the branchy
 // stage of DIFFERENT images side by side: every worker owns a decoder (its pinned coefficient planes are reused from
@@ -1434,8 +1447,8 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
     std::atomic<int> failed{0};
     // decoders (with their pinned coefficient planes) are kept between calls: page-locking and releasing 25 MB per
     // image and thread costs more than decoding it, and both serialise in the driver
-    static std::mutex idle_mu;
-    static std::vector<zj_decoder *> idle;
+    std::mutex &idle_mu = g_idle_mu;
+    std::vector<zj_decoder *> &idle = g_idle;
     auto take_decoder = [&]() -> zj_decoder * {
         zj_decoder *d = nullptr;
         {
