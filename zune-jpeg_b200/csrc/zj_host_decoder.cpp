@@ -1590,6 +1590,43 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     }
 
     lap("headers + marker scan", nullptr);
+    // ---- the host route (zj_decode_batch) for a list of images.  Those that cannot use the GPU entropy stage at all (no DRI,
+    // progressive, header errors) start on it right away, on the host threads, while the GPU works on the others.
+    auto run_host = [&](const std::vector<size_t> &rest) -> int {
+        if (rest.empty()) return 0;
+        std::vector<const uint8_t *> b2(rest.size());
+        std::vector<size_t> l2(rest.size()), ol2(rest.size());
+        std::vector<uint8_t *> o2(rest.size());
+        std::vector<int> s2(rest.size(), 0);
+        for (size_t t = 0; t < rest.size(); t++) {
+            b2[t] = bufs[rest[t]]; l2[t] = lens[rest[t]];
+            o2[t] = dev_out ? nullptr : out[rest[t]];          // device outputs: decoded into host memory first, then uploaded
+            ol2[t] = dev_out ? 0 : out_len[rest[t]];
+        }
+        int f = zj_decode_batch(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data());
+        if (f < 0) return f;
+        for (size_t t = 0; t < rest.size(); t++) {
+            const size_t i = rest[t];
+            if (!dev_out) { out[i] = o2[t]; out_len[i] = ol2[t]; status[i] = s2[t]; continue; }
+            int rc = s2[t];
+            if (rc == ZJ_OK) {
+                if (!out[i]) rc = ZJ_ERR_INVALID_ARG;
+                else if (out_len[i] < ol2[t]) rc = ZJ_ERR_SHORT_OUTPUT;
+                else if (cudaMemcpy(out[i], o2[t], ol2[t], cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); rc = ZJ_ERR_CUDA; }
+                if (rc != ZJ_OK) f++;
+            }
+            free(o2[t]);
+            out_len[i] = rc == ZJ_OK ? ol2[t] : 0;
+            status[i] = rc;
+        }
+        return f;
+    };
+    std::vector<char> is_early(n, 0);
+    std::vector<size_t> early_list;
+    for (size_t i = 0; i < n; i++) if (!items[i].gpu) { is_early[i] = 1; early_list.push_back(i); }
+    int early_rc = 0;
+    std::thread early;
+    if (!early_list.empty()) early = std::thread([&]() { cudaSetDevice(opt.device); early_rc = run_host(early_list); });
     // ---- GPU: sub-batches of as many images as fit the staging budget, two slots in flight.  Stage 1 of sub-batch b (upload,
     // clear the planes, entropy kernel, status download) is queued before the host waits for the statuses of sub-batch b-1 and
     // queues its stage 2 (reconstruction, pixel download), so the two streams keep the GPU and both PCIe directions busy.
@@ -1814,39 +1851,17 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
             out_len[i] = items[i].need;
         } else {
             if (malloced[i]) { free(malloced[i]); malloced[i] = nullptr; }
-            rest.push_back(i);
+            if (!is_early[i]) rest.push_back(i);
         }
     }
     if (n_gpu_entropy) *n_gpu_entropy = n_gpu;
-    // ---- everything else: the host stage
-    if (!rest.empty()) {
-        std::vector<const uint8_t *> b2(rest.size());
-        std::vector<size_t> l2(rest.size()), ol2(rest.size());
-        std::vector<uint8_t *> o2(rest.size());
-        std::vector<int> s2(rest.size(), 0);
-        for (size_t t = 0; t < rest.size(); t++) {
-            b2[t] = bufs[rest[t]]; l2[t] = lens[rest[t]];
-            o2[t] = dev_out ? nullptr : out[rest[t]];          // device outputs: decoded into host memory first, then uploaded
-            ol2[t] = dev_out ? 0 : out_len[rest[t]];
-        }
-        int f = zj_decode_batch(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data());
-        if (f < 0) return f;
-        for (size_t t = 0; t < rest.size(); t++) {
-            const size_t i = rest[t];
-            if (!dev_out) { out[i] = o2[t]; out_len[i] = ol2[t]; status[i] = s2[t]; continue; }
-            int rc = s2[t];
-            if (rc == ZJ_OK) {
-                if (!out[i]) rc = ZJ_ERR_INVALID_ARG;
-                else if (out_len[i] < ol2[t]) rc = ZJ_ERR_SHORT_OUTPUT;
-                else if (cudaMemcpy(out[i], o2[t], ol2[t], cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); rc = ZJ_ERR_CUDA; }
-                if (rc != ZJ_OK) f++;
-            }
-            free(o2[t]);
-            out_len[i] = rc == ZJ_OK ? ol2[t] : 0;
-            status[i] = rc;
-        }
-        failed += f;
-    }
+    // ---- the images the GPU turned down: the host stage
+    if (early.joinable()) early.join();
+    if (early_rc < 0) return early_rc;
+    failed += early_rc;
+    const int late_rc = run_host(rest);
+    if (late_rc < 0) return late_rc;
+    failed += late_rc;
     return failed;
 }
 
