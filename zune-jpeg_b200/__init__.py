@@ -5,11 +5,12 @@ from ._ffi import (  # noqa: F401
     VARIANT_SCALAR, VARIANT_X86, ZjComponent, ZjImage, ZjImageInfo, ZjOptions,
 )
 
-__all__ = ["Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "reconstruct", "decode_batch"]
+__all__ = ["Decoder", "ZuneJpegOptions", "JpegDecoder", "DecoderOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "reconstruct", "decode_batch"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require the built library
-    if name in ("Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "UnsupportedSchemes", "decode_batch"):
+    if name in ("Decoder", "ZuneJpegOptions", "ColorSpace", "DecodeErrors", "ImageInfo", "UnsupportedSchemes", "decode_batch",
+                "JpegDecoder", "DecoderOptions"):
         from . import decoder as _d
         return getattr(_d, name)
     if name in ("reconstruct", "Batch", "DeviceBuffer", "PinnedBuffer", "make_image"):

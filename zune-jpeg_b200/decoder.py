@@ -280,6 +280,11 @@ DecoderOptions = ZuneJpegOptions
 UnsupportedSchemes = enum.Enum("UnsupportedSchemes", "ExtendedSequentialHuffman LosslessHuffman ExtendedSequentialDctArithmetic ProgressiveDctArithmetic LosslessArithmetic")
 
 
+# names of later zune-jpeg releases (BASELINE north_star: `JpegDecoder::new(..).decode()/decode_into()` + `DecoderOptions`)
+JpegDecoder = Decoder
+DecoderOptions = ZuneJpegOptions
+
+
 def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None, gpu_entropy: bool = False, stats: dict | None = None,
                  device_out=None):
     """zj_decode_batch: JPEG byte strings in, pixel bytes out, `threads` host threads (0 = one per hardware thread)
