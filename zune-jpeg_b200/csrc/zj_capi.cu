@@ -431,7 +431,10 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
     cudaStream_t user = (cudaStream_t)stream;
     constexpr int NS_MAX = 4;
     const char *env_ns = getenv("ZJ_E2E_STREAMS"), *env_mb = getenv("ZJ_E2E_BUDGET_MB");
-    const int NS = std::max(1, std::min(NS_MAX, env_ns ? atoi(env_ns) : 3));
+    // ZJ_E2E_PIPE=1: one stream per direction (uploads / kernels / downloads) over a ring of four staging buffers chained by
+    // events, instead of whole sub-batches alternating over the streams
+    const bool pipe = getenv("ZJ_E2E_PIPE") != nullptr && atoi(getenv("ZJ_E2E_PIPE")) != 0;
+    const int NS = pipe ? 3 : std::max(1, std::min(NS_MAX, env_ns ? atoi(env_ns) : 3));
     cudaStream_t st[NS_MAX];
     // the staging streams are created once per host thread and device and reused: creating / destroying streams takes
     // driver-wide locks, which hurts when many threads call in (zj_decode_batch)
@@ -442,6 +445,8 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         cudaStream_t s[64][NS_MAX] = {};
         uint8_t *buf[64][NS_MAX] = {};
         size_t cap[64][NS_MAX] = {};
+        cudaEvent_t ev[64][NS_MAX][3] = {};   // per staging buffer: planes uploaded / kernels done / pixels downloaded
+        bool ev_rec[64][NS_MAX] = {};
     };
     // A thread leases a cache for its lifetime and hands it back when it exits (zj_decode_batch starts fresh worker threads
     // in every call: a plain thread_local would strand its streams and device buffers with every one of them).
@@ -499,12 +504,22 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
             bytes += need + 4 * 256;
             j++;
         }
-        cudaStream_t s = st[which];
-        which = (which + 1) % NS;
-        const int slot = (which + NS - 1) % NS;          // index of stream s
+        cudaStream_t s = st[pipe ? 0 : which];
+        which = (which + 1) % (pipe ? NS_MAX : NS);
+        const int slot = (which + (pipe ? NS_MAX : NS) - 1) % (pipe ? NS_MAX : NS);          // index of stream s / of the staging buffer
+        cudaStream_t s_up = pipe ? st[0] : s, s_k = pipe ? st[1] : s, s_dn = pipe ? st[2] : s;
         cudaError_t e = cudaSuccess;
+        if (pipe) {
+            for (int q = 0; q < 3; q++)
+                if (!cache.ev[device][slot][q]) CU(cudaEventCreateWithFlags(&cache.ev[device][slot][q], cudaEventDisableTiming));
+            // the buffer is free once the pixels of its last sub-batch have been downloaded
+            if (cache.ev_rec[device][slot]) CU(cudaStreamWaitEvent(s_up, cache.ev[device][slot][2], 0));
+        }
         if (cache.cap[device][slot] < bytes) {
-            if (cache.buf[device][slot]) { cudaStreamSynchronize(s); cudaFree(cache.buf[device][slot]); cache.buf[device][slot] = nullptr; cache.cap[device][slot] = 0; }
+            if (cache.buf[device][slot]) {
+                if (pipe) { for (int q = 0; q < 3; q++) cudaStreamSynchronize(st[q]); } else cudaStreamSynchronize(s);
+                cudaFree(cache.buf[device][slot]); cache.buf[device][slot] = nullptr; cache.cap[device][slot] = 0;
+            }
             e = cudaMalloc((void **)&cache.buf[device][slot], bytes + bytes / 8);
             if (e != cudaSuccess) { cache.buf[device][slot] = nullptr; rc = cuda_fail(e, "cudaMalloc(staging)"); break; }
             cache.cap[device][slot] = bytes + bytes / 8;
@@ -515,28 +530,38 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         std::vector<size_t> dlens(j - i);
         size_t off = 0;
         auto take = [&](size_t nbytes) { uint8_t *p = pool + off; off += (nbytes + 255) & ~(size_t)255; return p; };
-        for (size_t k = i; k < j && rc == ZJ_OK; k++) {
+        // device addresses first, then the descriptors, then the copies: the descriptor upload comes from pageable memory, and such a
+        // copy first waits for everything queued on its stream -- behind the plane uploads it would hold the host back until they
+        // are done, and nothing of the next sub-batch could be queued meanwhile
+        for (size_t k = i; k < j; k++) {
             for (uint32_t z = 0; z < plans[k].ncomp_used; z++) {
                 const size_t nb = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
-                uint8_t *p = take(nb);
-                e = cudaMemcpyAsync(p, imgs[k].comp[z].coeff, nb, cudaMemcpyHostToDevice, s);
-                if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
-                dimgs[k - i].comp[z].coeff = (const int16_t *)p;
+                dimgs[k - i].comp[z].coeff = (const int16_t *)take(nb);
             }
             douts[k - i] = take(plans[k].out_size);
             dlens[k - i] = plans[k].out_size;
         }
-        if (rc != ZJ_OK) break;
         zj_batch *b = nullptr;
-        rc = batch_create_impl(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b, true, s);
+        rc = batch_create_impl(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b, true, s_k);
         if (rc != ZJ_OK) break;
+        for (size_t k = i; k < j && rc == ZJ_OK; k++) {
+            for (uint32_t z = 0; z < plans[k].ncomp_used; z++) {
+                const size_t nb = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
+                e = cudaMemcpyAsync((void *)dimgs[k - i].comp[z].coeff, imgs[k].comp[z].coeff, nb, cudaMemcpyHostToDevice, s_up);
+                if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+            }
+        }
+        if (rc != ZJ_OK) { zj_batch_destroy(b); break; }
         pd->batches.push_back(b);
-        rc = zj_batch_run(b, s);
+        if (pipe) { CU(cudaEventRecord(cache.ev[device][slot][0], s_up)); CU(cudaStreamWaitEvent(s_k, cache.ev[device][slot][0], 0)); }
+        rc = zj_batch_run(b, s_k);
         if (rc != ZJ_OK) break;
+        if (pipe) { CU(cudaEventRecord(cache.ev[device][slot][1], s_k)); CU(cudaStreamWaitEvent(s_dn, cache.ev[device][slot][1], 0)); }
         for (size_t k = i; k < j; k++) {
-            e = cudaMemcpyAsync(out[k], douts[k - i], plans[k].out_size, cudaMemcpyDeviceToHost, s);
+            e = cudaMemcpyAsync(out[k], douts[k - i], plans[k].out_size, cudaMemcpyDeviceToHost, s_dn);
             if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
         }
+        if (pipe && rc == ZJ_OK) { CU(cudaEventRecord(cache.ev[device][slot][2], s_dn)); cache.ev_rec[device][slot] = true; }
         i = j;
     }
     if (rc == ZJ_OK) {
