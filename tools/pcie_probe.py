@@ -4,7 +4,8 @@ import sys
 import time
 import torch
 
-n = 1 << 30
+import os
+n = int(os.environ.get("PROBE_GB", "1")) << 30   # PROBE_GB=6: buffers of the size the bench's e2e leg moves per step
 h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
 h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
 d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
@@ -29,5 +30,5 @@ def run(h2d, d2h, chunk, reps=5):
 
 
 run(True, True, n, 1)
-for chunk in [n] + [int(a) << 20 for a in sys.argv[1:]] if len(sys.argv) > 1 else [n, 64 << 20, 16 << 20, 4 << 20]:
+for chunk in ([n] + [int(a) << 20 for a in sys.argv[1:]]) if len(sys.argv) > 1 else [n, 64 << 20, 16 << 20, 4 << 20]:
     print("chunk %5d MB: H2D alone %.1f  D2H alone %.1f  both at once %.1f GB/s each" % (chunk >> 20, run(True, False, chunk), run(False, True, chunk), run(True, True, chunk)), flush=True)
