@@ -352,6 +352,11 @@ def test_gpu_entropy_decode_matches_host_stage():
     flip = bytearray(base); flip[len(flip) // 2] ^= 0x10
     cases.append((bytes(flip), None))                                                          # damaged entropy data: either route
     cases.append((bytes([0xff, 0xd8, 0xa4]), False))                                           # header error
+    fill = bytearray(base)                                                                     # 0xFF fill bytes in front of every RSTn (legal)
+    sos = base.index(b"\xff\xda")
+    for k, p_ in enumerate(reversed([i for i in range(sos, len(base) - 1) if base[i] == 0xFF and 0xD0 <= base[i + 1] <= 0xD7])):
+        fill[p_:p_] = b"\xff" * (1 + k % 3)
+    cases.append((bytes(fill), True))
     jpegs = [c[0] for c in cases]
     for out_cs in (ColorSpace.RGB, ColorSpace.RGBA, ColorSpace.GRAYSCALE):
         opts = ZuneJpegOptions().set_out_colorspace(out_cs)

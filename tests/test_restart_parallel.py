@@ -94,3 +94,17 @@ def test_small_intervals_many_segments():
 def test_batch_uses_spare_threads():
     from zune_jpeg_b200 import _ffi
     assert hasattr(_ffi.load(), "zj_decoder_entropy_segments")
+
+
+def test_fill_bytes_before_markers():
+    """0xFF fill bytes in front of RSTn (legal, B.1.1.2): the marker scan and the bit reader (bitstream.rs:200-215) agree on where
+    the next interval starts, so the intervals still run side by side."""
+    data = bytearray(jpeg_util.synth_jpeg(16, 1024, 512, "420", quality=85, restart_rows=1))
+    sos = bytes(data).index(b"\xff\xda")
+    marks = [i for i in range(sos, len(data) - 1) if data[i] == 0xFF and 0xD0 <= data[i + 1] <= 0xD7]
+    for k, p in enumerate(reversed(marks)):
+        data[p:p] = b"\xff" * (1 + k % 3)
+    n, res = _same(bytes(data))
+    assert res[0] == "ok" and n == 512 // 16
+    clean, _ = _decode(jpeg_util.synth_jpeg(16, 1024, 512, "420", quality=85, restart_rows=1), 1)
+    assert res == clean
