@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the pixel-reconstruction path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3_444|c3_gray|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3_444|c3_gray|c4|c5]
 
 A "step" is one pass of the hot path (dequant + IDCT + upsample + YCbCr->RGB, reference src/worker.rs:32)
 over one batch of synthetic images.  Default workload = BASELINE.json configs[1]: a batch of 256 synthetic
@@ -37,13 +37,28 @@ import numpy as np  # noqa: E402
 
 CONFIGS = {
     # name: (width, height, subsampling, progressive, gray, out_cs, default batch, description)
+    "c1": (1920, 1080, "444", False, False, 0, 256, "tests/golden/ref/test-baseline.jpg (the reference's test-images/test-baseline.jpg: 1920x1080 baseline, really 4:4:4) batch of 256 copies -> RGB (BASELINE configs[0])"),
     "c2": (3840, 2160, "420", False, False, 0, 256, "3840x2160 baseline 4:2:0 JPEG batch of 256 -> RGB (BASELINE configs[1])"),
     "c3_444": (4096, 4096, "444", False, False, 0, 32, "4096x4096 baseline 4:4:4 JPEG batch -> RGB (BASELINE configs[2])"),
     "c3_gray": (4096, 4096, "444", False, True, 1, 64, "4096x4096 grayscale JPEG batch -> gray (BASELINE configs[2])"),
     "c4": (1920, 1080, "422", True, False, 0, 256, "1920x1080 progressive 4:2:2 JPEG batch -> RGB (BASELINE configs[3])"),
     "c5": (8192, 8192, "420", False, False, 5, 16, "8192x8192 baseline 4:2:0 + restart markers batch -> RGBA (BASELINE configs[4])"),
 }
-B_PER_PX = {"c2": 6, "c3_444": 9, "c3_gray": 3, "c4": 7, "c5": 7}  # 2 B x samples/px + out B/px
+B_PER_PX = {"c1": 9, "c2": 6, "c3_444": 9, "c3_gray": 3, "c4": 7, "c5": 7}  # 2 B x samples/px + out B/px
+
+
+KERNEL_OF = {"c1": "zj::reconstruct_fast_kernel<MODE_NONE>", "c2": "zj::reconstruct_fast_kernel<MODE_HV>", "c3_444": "zj::reconstruct_fast_kernel<MODE_NONE>",
+             "c3_gray": "zj::gray_fast_kernel", "c4": "zj::reconstruct_fast_kernel<MODE_H>", "c5": "zj::reconstruct_fast_kernel<MODE_HV>"}
+
+
+def kernel_sha16() -> str:
+    """hash of the sources the reconstruction kernels are built from (profiles/traffic.json is keyed by it)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("zj_kernels.cu", "zj_device.h"):
+        with open(os.path.join(ROOT, "zune-jpeg_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def metric_name() -> str:
@@ -60,15 +75,40 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def physical_cores() -> int:
+    """distinct physical cores among the CPUs this process may run on (SMT siblings counted once)"""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        seen = set()
+        for c in cpus:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                seen.add(f.read().strip())
+        return max(1, len(seen))
+    except Exception:
+        return host_threads()
+
+
+def cpu_threads() -> int:
+    """threads of the CPU port's persistent strip pool: one per physical core (more only oversubscribes the SIMD units and
+    made the baseline move by 25 % from box to box)"""
+    return max(1, min(host_threads(), physical_cores()))
+
+
+REF_FIXTURE = os.path.join(ROOT, "tests", "golden", "ref", "test-baseline.jpg")
+
+
 def make_pool(cfg: str, n_distinct: int, rank: int):
-    """n_distinct synthetic JPEGs -> host stage -> (descriptor, planes) per image."""
+    """n_distinct synthetic JPEGs (c1: the reference's own file) -> host stage -> (descriptor, planes) per image."""
     import jpeg_util
     from zune_jpeg_b200.decoder import ColorSpace, Decoder, ZuneJpegOptions
     w, h, sub, prog, gray, out_cs, _, _ = CONFIGS[cfg]
     from concurrent.futures import ThreadPoolExecutor
 
     def one(i):
-        data = jpeg_util.synth_jpeg(1000 * rank + i, w, h, sub, 90, prog, gray, restart_rows=1 if cfg == "c5" else 0)
+        if cfg == "c1":
+            data = open(REF_FIXTURE, "rb").read()
+        else:
+            data = jpeg_util.synth_jpeg(1000 * rank + i, w, h, sub, 90, prog, gray, restart_rows=1 if cfg == "c5" else 0)
         d = Decoder.new_with_options(ZuneJpegOptions().set_out_colorspace(ColorSpace(out_cs)))
         img, planes = d.decode_coefficients(data)
         return img, planes, data
@@ -217,7 +257,7 @@ def run_reference(args):
         return
     cfg = args.config
     w, h = CONFIGS[cfg][0], CONFIGS[cfg][1]
-    threads = host_threads()
+    threads = cpu_threads()
     n_sample = 8 if w * h <= 3840 * 2160 else 2
     pool = make_pool(cfg, n_sample, 0)
     import oracle
@@ -244,7 +284,7 @@ def run_reference(args):
         "impl": "reference", "metric": metric_name(), "value": round(value, 2), "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": CONFIGS[cfg][7], "sample": sample, "threads": threads,
+        "config": {"workload": CONFIGS[cfg][7], "sample": sample, "threads": threads, "host_threads": host_threads(), "physical_cores": physical_cores(),
                    "note": "reference is Rust (no rustc/cargo here): this is the C oracle port of the same path, real AVX2/SSE4.1 intrinsics, strip-parallel"},
         "cpu_baseline": {"value": round(value, 2), "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -336,6 +376,25 @@ def run_ours(args):
     total_mp = pl.sum(mp_step * args.steps)
     value = total_mp / (ms_max / 1e3)
 
+    # ---- sustained: the same launch back to back for >= args.sustain_seconds (the 20-step region above is a burst of ~70 ms;
+    # this shows what the kernel holds once power / clocks have settled), clocks sampled during it
+    sustained = None
+    if args.sustain_seconds > 0 and rank == 0:
+        n_s = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1)
+        s2 = ClockSampler(device)
+        s2.start()
+        s2.mark()
+        e0, e1 = gpu.Event(device), gpu.Event(device)
+        e0.record(stream.ptr)
+        for _ in range(n_s):
+            plan.run(stream.ptr)
+        e1.record(stream.ptr)
+        stream.synchronize()
+        ms_s = e0.elapsed_ms(e1)
+        ck = s2.stop()
+        sustained = {"value": round(mp_step * n_s / (ms_s / 1e3), 2), "unit": "MP/s", "launches": n_s, "seconds": round(ms_s / 1e3, 3),
+                     "ms_per_step": round(ms_s / n_s, 4), "roofline_frac": None, "clocks": ck}
+
     # ---- e2e: zj_gpu_reconstruct with pinned HOST planes and pinned HOST outputs (H2D + kernels + D2H timed)
     e2e = None
     if not args.no_e2e:
@@ -391,12 +450,16 @@ def run_ours(args):
                 raise SystemExit("bench.py: e2e output differs from the oracle")
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores, bounded sample
-    cpu = None
+    cpu, cpu_4t = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = host_threads()
+        threads = cpu_threads()
         v, n = time_cpu_port(pool, args.cpu_seconds, threads)
-        cpu = {"value": round(v, 2), "unit": "MP/s", "cores": threads, "kind": "port",
-               "sample": f"{n} images ({n_distinct} distinct {w}x{h}, repeated for >= {args.cpu_seconds:.0f} s), planes in RAM -> pixels in RAM, oracle X86 variant, strip-parallel"}
+        cpu = {"value": round(v, 2), "unit": "MP/s", "cores": threads, "kind": "port", "host_threads": host_threads(), "physical_cores": physical_cores(),
+               "sample": f"{n} images ({n_distinct} distinct {w}x{h}, repeated for >= {args.cpu_seconds:.0f} s), planes in RAM -> pixels in RAM, oracle X86 variant, strip-parallel (persistent pool, one thread per physical core)"}
+        # the reference's default (ZuneJpegOptions::num_threads = 4, /root/reference/src/options.rs:33)
+        v4, n4 = time_cpu_port(pool, max(3.0, args.cpu_seconds / 3), min(4, host_threads()))
+        cpu_4t = {"value": round(v4, 2), "unit": "MP/s", "cores": min(4, host_threads()), "kind": "port",
+                  "sample": f"{n4} images, same path, the reference's default of 4 threads (options.rs:33)"}
 
     # ---- whole decode (SURVEY 8(f) "next" row, informational): JPEG bytes -> pixels through zj_decode_batch, i.e. the
     # host threads entropy-decode different images while the GPU reconstructs the finished ones; beside it the CPU-only
@@ -532,15 +595,28 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_ms = ms / max(launches, 1)
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
-    traffic = None
+    # measured DRAM bytes per launch (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum) are kept per config in
+    # profiles/traffic.json TOGETHER WITH the hash of the kernel sources they were captured with: a figure taken from another
+    # kernel is not reported
+    traffic, traffic_note = None, None
+    ksha = kernel_sha16()
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
-    except Exception:
-        pass
+        ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
+        if ent is None:
+            traffic_note = "no ncu capture for this config"
+        elif ent.get("kernel_sha16") == ksha:
+            traffic = ent["dram_bytes_per_launch"]
+            traffic_note = ent.get("source")
+        else:
+            traffic_note = f"stale: profiles/traffic.json holds {ent.get('dram_bytes_per_launch')} B captured with kernel sources {ent.get('kernel_sha16')}, these are {ksha}"
+    except Exception as e:
+        traffic_note = f"profiles/traffic.json unreadable: {e}"
+    if sustained is not None:
+        sustained["roofline_frac"] = round(algo_bytes / (sustained["ms_per_step"] / 1e3) / 1e9 / peak, 4)
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": traffic, "traffic_note": traffic_note, "kernel_sha16": ksha, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(kernel_ms, 4),
-                "kernel": ("zj::gray_kernel" if cfg == "c3_gray" else "zj::reconstruct_fast_kernel") + " (one launch per step covers the whole batch)"}
+                "kernel": KERNEL_OF[cfg] + " (one launch per step covers the whole batch)"}
 
     if rank == 0:
         line = {
@@ -551,7 +627,7 @@ def run_ours(args):
                        "variant": "X86 (use_unsafe=true)", "bytes_per_px": B_PER_PX[cfg],
                        "l2": f"inputs {algo_bytes / 1e9:.2f} GB per step per GPU, far larger than the 126 MB L2 (no flush needed)",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decode": decode, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_4t": cpu_4t, "sustained": sustained, "decode": decode, "clocks": clocks,
             "checked_vs_oracle": check, "setup_s": round(time.perf_counter() - t_setup, 1),
         }
         print(json.dumps(line))
@@ -569,6 +645,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic JPEGs cycled through the batch")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the back-to-back `sustained` leg (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the whole-decode (JPEG bytes -> pixels) measurement")

@@ -256,6 +256,16 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
  * that take the host route are uploaded after decoding.  The call returns when all pixels are in place. */
 ZJ_API int zj_decode_batch_gpu_device(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                                       uint8_t *const *out_dev, size_t *out_len, int *status, size_t *n_gpu_entropy);
+/* TEST-ONLY switches for three bugs of the reference's host stage that this library reproduces by default so that its
+ * coefficient planes are the reference's.  A cleared bit makes the cited lines behave like libjpeg:
+ *   Q9  src/huffman.rs:249-252   fast-AC entry `(k << 10) + ...` is an i16: |k| >= 32 loses its top bits
+ *   Q10 src/bitstream.rs:278-281 decode_dc refills only below 16 buffered bits but may consume 27: the reader under-runs
+ *   Q11 src/mcu.rs:337-342       the MCU loop breaks on a PREFETCHED EOI: trailing components of the last MCU stay zero
+ * Process-wide; takes effect for tables built / streams started afterwards.  With any bit cleared the GPU entropy route
+ * (zj_decode_batch_gpu*) sends every image through the host stage.  tests/test_quirks.py is the only caller. */
+enum { ZJ_QUIRK_Q9_FAST_AC_I16 = 1u, ZJ_QUIRK_Q10_DC_REFILL = 2u, ZJ_QUIRK_Q11_EOI_BREAK = 4u, ZJ_QUIRK_ALL = 7u };
+ZJ_API void zj_host_set_quirks(uint32_t mask);
+ZJ_API uint32_t zj_host_get_quirks(void);
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d);                 /* zj_decode_error_kind                */
 ZJ_API const char *zj_decoder_error(const zj_decoder *d);              /* Display text of the DecodeErrors    */
 

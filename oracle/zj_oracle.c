@@ -13,6 +13,7 @@
 #include "zj_oracle.h"
 
 #include <pthread.h>
+#include <stdatomic.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -852,13 +853,15 @@ size_t zjo_output_size(const zj_image *img)
     return g.out_size;
 }
 
+/* Strip-parallel driver (the role of scoped_threadpool in mcu.rs:135,356-368 / mcu_prog.rs:196-233): a PERSISTENT pool --
+ * workers are created once and woken per image, strips are handed out by an atomic counter -- so that the CPU baseline
+ * bench.py times does not pay thread creation per image or a lock per strip. */
 typedef struct {
     const zj_image *img;
     const geometry *g;
     uint8_t *out;
-    size_t next;         /* next strip to take */
-    int rc;
-    pthread_mutex_t mu;
+    atomic_size_t next;  /* next strip to take */
+    atomic_int rc;
 } strip_job;
 
 static int run_strip(const zj_image *img, const geometry *g, uint8_t *out, size_t s)
@@ -885,21 +888,44 @@ static int run_strip(const zj_image *img, const geometry *g, uint8_t *out, size_
     return rc;
 }
 
-static void *strip_worker(void *p)
+static void run_strips(strip_job *job)
 {
-    strip_job *job = (strip_job *)p;
     for (;;) {
-        pthread_mutex_lock(&job->mu);
-        size_t s = job->next++;
-        int stop = job->rc != ZJO_OK;
-        pthread_mutex_unlock(&job->mu);
-        if (stop || s >= job->g->n_strips) break;
+        if (atomic_load_explicit(&job->rc, memory_order_relaxed) != ZJO_OK) break;
+        size_t s = atomic_fetch_add_explicit(&job->next, 1, memory_order_relaxed);
+        if (s >= job->g->n_strips) break;
         int rc = run_strip(job->img, job->g, job->out, s);
-        if (rc != ZJO_OK) {
-            pthread_mutex_lock(&job->mu);
-            if (job->rc == ZJO_OK) job->rc = rc;
-            pthread_mutex_unlock(&job->mu);
-        }
+        if (rc != ZJO_OK) { int ok = ZJO_OK; atomic_compare_exchange_strong(&job->rc, &ok, rc); }
+    }
+}
+
+#define ZJO_MAX_THREADS 256
+static struct {
+    pthread_mutex_t call;              /* one image at a time uses the pool */
+    pthread_mutex_t mu;
+    pthread_cond_t work, done;
+    int n_workers;                     /* threads created so far */
+    int wanted;                        /* workers that should take part in the current job */
+    unsigned generation;
+    int running;                       /* workers still inside the current job */
+    strip_job *job;
+    pthread_t th[ZJO_MAX_THREADS];
+} pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, 0, 0, NULL, {0}};
+
+static void *pool_worker(void *p)
+{
+    const int id = (int)(intptr_t)p;
+    unsigned seen = 0;
+    pthread_mutex_lock(&pool.mu);
+    for (;;) {
+        while (pool.generation == seen) pthread_cond_wait(&pool.work, &pool.mu);
+        seen = pool.generation;
+        if (id >= pool.wanted) continue;
+        strip_job *job = pool.job;
+        pthread_mutex_unlock(&pool.mu);
+        run_strips(job);
+        pthread_mutex_lock(&pool.mu);
+        if (--pool.running == 0) pthread_cond_signal(&pool.done);
     }
     return NULL;
 }
@@ -925,14 +951,28 @@ int zjo_reconstruct_image(const zj_image *img, uint8_t *out, size_t out_len, int
         }
         return ZJO_OK;
     }
-    strip_job job = {img, &g, out, 0, ZJO_OK, PTHREAD_MUTEX_INITIALIZER};
-    if (threads > 256) threads = 256;
-    pthread_t th[256];
-    int started = 0;
-    for (int i = 0; i < threads; i++) {
-        if (pthread_create(&th[started], NULL, strip_worker, &job) == 0) started++;
+    strip_job job;
+    job.img = img; job.g = &g; job.out = out;
+    atomic_init(&job.next, 0);
+    atomic_init(&job.rc, ZJO_OK);
+    if (threads > ZJO_MAX_THREADS) threads = ZJO_MAX_THREADS;
+    pthread_mutex_lock(&pool.call);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.n_workers < threads - 1) {   /* the caller is the last worker */
+        if (pthread_create(&pool.th[pool.n_workers], NULL, pool_worker, (void *)(intptr_t)pool.n_workers) != 0) break;
+        pthread_detach(pool.th[pool.n_workers]);
+        pool.n_workers++;
     }
-    if (started == 0) strip_worker(&job);
-    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
-    return job.rc;
+    pool.wanted = threads - 1 < pool.n_workers ? threads - 1 : pool.n_workers;
+    pool.running = pool.wanted;
+    pool.job = &job;
+    pool.generation++;
+    pthread_cond_broadcast(&pool.work);
+    pthread_mutex_unlock(&pool.mu);
+    run_strips(&job);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.running > 0) pthread_cond_wait(&pool.done, &pool.mu);
+    pthread_mutex_unlock(&pool.mu);
+    pthread_mutex_unlock(&pool.call);
+    return atomic_load(&job.rc);
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("ZJ_LIB_PATH") or os.path.join(_HERE, "csrc", "libzune
 CS_RGB, CS_GRAYSCALE, CS_YCBCR, CS_CMYK, CS_YCCK, CS_RGBA, CS_RGBX = range(7)
 VARIANT_X86, VARIANT_SCALAR = 0, 1
 FLAG_PROGRESSIVE = 1
+QUIRK_Q9, QUIRK_Q10, QUIRK_Q11, QUIRK_ALL = 1, 2, 4, 7   # zj_host_set_quirks (tests only)
 OK = 0
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_SHORT_PLANE, ERR_SHORT_OUTPUT = -1, -2, -3, -4
 ERR_REF_PANIC, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_DECODE = -5, -6, -7, -8, -9
@@ -119,6 +120,8 @@ SYMBOLS = {
     "zj_decode_batch_gpu_device": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
                                              C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "zj_release_host_caches": (None, []),
+    "zj_host_set_quirks": (None, [C.c_uint32]),
+    "zj_host_get_quirks": (C.c_uint32, []),
     "zj_decoder_entropy_segments": (C.c_size_t, [_P]),
     "zj_decoder_error_kind": (C.c_int, [_P]),
     "zj_decoder_error": (C.c_char_p, [_P]),

@@ -132,6 +132,12 @@ struct Cursor {  // std::io::Cursor<Vec<u8>> as the reference uses it
 // ------------------------------------------------------------------------------------------------ Huffman
 constexpr int HUFF_LOOKAHEAD = 9;  // src/huffman.rs:9
 
+// Host-stage quirks of the reference, reproduced by default.  zj_host_set_quirks() clears bits for
+// TESTS ONLY: with a bit cleared the corresponding lines behave the way libjpeg does, which is how tests/test_quirks.py
+// shows that each deviation from libjpeg on the reference's own fixtures comes from exactly the cited lines.
+static std::atomic<uint32_t> g_quirks{ZJ_QUIRK_ALL};
+static inline bool quirk(uint32_t bit) { return (g_quirks.load(std::memory_order_relaxed) & bit) != 0; }
+
 struct HuffmanTable {  // src/huffman.rs:14-41
     int32_t maxcode[18];
     int32_t offset[18];
@@ -210,7 +216,10 @@ static void build_huffman(HuffmanTable &p, const uint8_t codes[17], const uint8_
                     int16_t kk = (int16_t)((((int16_t)i << len) & ((1 << HUFF_LOOKAHEAD) - 1)) >> (HUFF_LOOKAHEAD - mag_bits));
                     const int16_t m = (int16_t)(1 << (mag_bits - 1));
                     if (kk < m) kk = (int16_t)(kk + (int16_t)((int16_t)(~0u << mag_bits) + 1));
-                    if (kk >= -128 && kk <= 127) p.ac_lookup[i] = (int16_t)((kk << 10) + (run << 4) + (len + mag_bits));
+                    // Q9 (huffman.rs:249-252): the entry is an i16, so `k << 10` keeps only 6 bits of k: |k| >= 32 decodes wrong.
+                    // Quirk off: such values stay out of the fast table and take the general path below it.
+                    const int16_t lim = quirk(ZJ_QUIRK_Q9_FAST_AC_I16) ? 128 : 32;
+                    if (kk >= -lim && kk <= lim - 1) p.ac_lookup[i] = (int16_t)((kk << 10) + (run << 4) + (len + mag_bits));
                 }
             }
         }
@@ -229,6 +238,7 @@ struct BitStream {  // src/bitstream.rs:94-114
     Marker marker{};
     uint8_t successive_high = 0, successive_low = 0, spec_start = 0, spec_end = 0;
     int32_t eob_run = 0;
+    bool q10 = quirk(ZJ_QUIRK_Q10_DC_REFILL);   // decode_dc refills only below 16 buffered bits (bitstream.rs:278-281)
 
     static bool has_byte_ff(uint32_t b)  // has_byte(b, 255), bitstream.rs:705-717
     {
@@ -324,7 +334,9 @@ struct BitStream {  // src/bitstream.rs:94-114
     }
     void decode_dc(Cursor &r, const HuffmanTable &dc, int32_t &pred)  // bitstream.rs:272-297
     {
-        if (bits_left < 16) refill(r);
+        // Q10: a DC code (<= 16 bits) plus its magnitude bits (<= 11) can need 27 bits, but the refill happens only below 16:
+        // the reader under-runs and mis-syncs.  Quirk off: refill like the AC loop does (whenever <= 32 bits are buffered).
+        if (bits_left < 16 || !q10) refill(r);
         int32_t symbol = dc.lookup[peek_bits<HUFF_LOOKAHEAD>()];
         decode_huff(symbol, dc);
         if (symbol != 0) { const int32_t rr = get_bits((uint8_t)symbol); symbol = huff_extend(rr, symbol); }
@@ -923,7 +935,10 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
                 if (stream.has_marker) {  // mcu.rs:337-348
                     if (stream.marker.kind == M_EOI) {
                         if (SEGMENT && must_reset) throw SegmentAbnormal{};
-                        break;
+                        // Q11 (mcu.rs:337-342): the reader PREFETCHES, so EOI is usually "seen" while the last MCU still has
+                        // components to decode from buffered bits; the break drops them.  Quirk off: finish the MCU.
+                        if (quirk(ZJ_QUIRK_Q11_EOI_BREAK)) break;
+                        continue;
                     }
                     if (stream.marker.kind == M_RST) continue;
                     if (SEGMENT) throw SegmentAbnormal{};
@@ -1106,6 +1121,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
     bool gpu_entropy_prepare(const Cursor &reader, GpuPrep &pp)
     {
         if (is_progressive || restart_interval == 0 || todo != restart_interval) return false;
+        if (g_quirks.load() != ZJ_QUIRK_ALL) return false;   // the GPU form carries the quirks as written; test switches -> host stage
         if (reader.len >= 0xFFFFFFF0ull) return false;
         try { baseline_setup(pp.g); } catch (DecodeError &) { return false; }
         const BaselineGeom &g = pp.g;
@@ -1876,6 +1892,8 @@ ZJ_API int zj_decode_batch_gpu_device(const zj_options *o, const uint8_t *const 
     return decode_batch_gpu_impl(o, bufs, lens, n, const_cast<uint8_t **>(out_dev), out_len, status, n_gpu_entropy, true);
 }
 
+ZJ_API void zj_host_set_quirks(uint32_t mask) { g_quirks.store(mask & ZJ_QUIRK_ALL); }
+ZJ_API uint32_t zj_host_get_quirks(void) { return g_quirks.load(); }
 ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d) { return d ? d->last_entropy_segments : 0; }
 ZJ_API int zj_decoder_error_kind(const zj_decoder *d) { return d ? d->err_kind : ZJ_DE_NONE; }
 ZJ_API const char *zj_decoder_error(const zj_decoder *d) { return d ? d->err_display.c_str() : ""; }
