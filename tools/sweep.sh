@@ -3,7 +3,8 @@
 tag=$1; shift; list=$1; shift
 for it in $list; do
   v=${it%%:*}; s=${it##*:}
-  ZJ_LIB_PATH=build/variants/libzj_$v.so ZJ_SPC=$s python bench.py --no-e2e --no-cpu --no-decode --steps 10 "$@" > gpurun_out/${tag}_${v}_$s.json 2> gpurun_out/${tag}_${v}_$s.err
+  if [ "$s" = d ]; then unset ZJ_SPC; else export ZJ_SPC=$s; fi   # d = the launcher's own choice
+  ZJ_LIB_PATH=build/variants/libzj_$v.so python bench.py --no-e2e --no-cpu --no-decode --sustain-seconds 0 --steps 10 "$@" > gpurun_out/${tag}_${v}_$s.json 2> gpurun_out/${tag}_${v}_$s.err
   python - <<PY
 import json
 try:

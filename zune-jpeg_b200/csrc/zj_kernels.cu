@@ -361,6 +361,11 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
     }
 }
 
+#ifndef ZF_RP_UNROLL
+#define ZF_RP_UNROLL 1
+#endif
+#define ZF_PRAGMA(x) _Pragma(#x)
+#define ZF_UNROLL(n) ZF_PRAGMA(unroll n)
 template <typename AfterRows>
 __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, const u32 sc, const u32 *__restrict__ qtw, uint8_t *__restrict__ dst, const int dst_stride,
                                             AfterRows after_rows)
@@ -368,7 +373,7 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
     constexpr u32 CH = 16u * ZF_PRODUCERS;
     u32 acc = 0, dcmask = 0xffff0000u, dc0 = 0;
     bool rows45 = false, rows67 = false;       // warp-uniform: anything in rows 4-5 / 6-7 of any block of the warp
-#pragma unroll 1
+    ZF_UNROLL(ZF_RP_UNROLL)
     for (int rp = 0; rp < 4; rp++) {          // rows 2rp, 2rp+1
         u32 a0, a1, a2, a3, b0, b1, b2, b3;
         const u32 pa = sl ^ (u32)(rp << 5);
@@ -710,6 +715,29 @@ __device__ __forceinline__ void convert_pair(u32 y, u32 cb, u32 cr, u32 &r, u32 
     g = minrelu2(vadd2(y32 + 0x331F331Fu - cb * 11u - cr * 23u, 0xDE00DE00u), 0x1FFF1FFFu) >> 5;  // +13087, then -8704
     // 64y + 113cb reaches 48751 (> i16 range), so this channel is clamped as unsigned lanes: [14464, 30847] - 14464
     b = (minu2(maxu2(cb * 113u + (y32 << 1), 0x38803880u), 0x787F787Fu) - 0x38803880u) >> 6;
+}
+
+// The same with the results left in bytes 1 and 3 (ZF_CONV_HI): the final `>> 5` / `>> 6` (a shift: ALU pipe, the busier one in
+// the consumers) becomes `* 8` / `* 4` on lanes that are already clamped to 13 / 14 bits (a multiply: FMA pipe), and the byte
+// interleave picks bytes 1 and 3 instead of 0 and 2.  The blue channel is clamped from above as unsigned lanes first
+// (64y + 113cb reaches 48751), then shifted down by 14464 and clamped at zero as signed lanes: one instruction fewer.
+#ifndef ZF_CONV_HI
+#define ZF_CONV_HI 2
+#endif
+__device__ __forceinline__ void convert_pair_hi(u32 y, u32 cb, u32 cr, u32 &r, u32 &g, u32 &b, const u32 k)
+{
+    const u32 y32 = y << 5;
+#if ZF_CONV_HI == 2
+    // every channel is biased so that ONE lane constant (-16384, kept in a register by the caller) brings it back: the biases
+    // ride on immediates of 32-bit adds (all lanes stay inside [0, 65535], so the lanes never carry into each other)
+    r = minrelu2(vadd2(cr * 45u + y32 + 0x29802980u, k), 0x1FFF1FFFu) * 8u;                        // +10624 = 16384 - 5760
+    g = minrelu2(vadd2(y32 + 0x511F511Fu - cb * 11u - cr * 23u, k), 0x1FFF1FFFu) * 8u;             // +20767 = 16384 + 4352 + 31
+    b = minrelu2(vadd2(minu2(cb * 113u + y * 64u + 0x07800780u, 0x7FFF7FFFu), k), 0x3FFF3FFFu) * 4u;   // +1920 = 16384 - 14464
+#else
+    r = minrelu2(vadd2(cr * 45u + y32, 0xE980E980u), 0x1FFF1FFFu) * 8u;
+    g = minrelu2(vadd2(y32 + 0x331F331Fu - cb * 11u - cr * 23u, 0xDE00DE00u), 0x1FFF1FFFu) * 8u;
+    b = minrelu2(vadd2(minu2(cb * 113u + y * 64u, 0x787F787Fu), 0xC780C780u), 0x3FFF3FFFu) * 4u;   // min(., 30847) - 14464, relu
+#endif
 }
 
 // 8 pixels -> 24 interleaved bytes.  c0/c1/c2 hold channel pairs with the values in bytes 0 and 2.
@@ -1145,8 +1173,10 @@ __device__ __forceinline__ void hfilter16(u32 h, const u32 r[4], u32 E[4], u32 O
 // arrangement of hfilter16.  nw = number of leading 32-bit words to store (12, or fewer when the row's tail chunk
 // overwrites the rest, worker.rs:221-246); vec = 16-byte stores are aligned.
 __device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 cbE[4], const u32 cbO[4], const u32 crE[4], const u32 crO[4],
-                                       const bool ycc, const int nw, const bool vec)
+                                       const bool ycc, const int nw, const bool vec, const u32 sel, const u32 kk)
 {
+    // sel: byte selector of the first interleave step (the channel values sit in bytes 1 and 3 after convert_pair_hi, in bytes
+    // 0 and 2 otherwise); kk: the lane constant of convert_pair_hi -- both held in registers by the caller
     u32 w[12];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -1155,12 +1185,17 @@ __device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 
         if (ycc) {  // `as u8` interleave (color_convert/scalar.rs:152-161)
             c0E = yE; c1E = cbE[k]; c2E = crE[k]; c0O = yO; c1O = cbO[k]; c2O = crO[k];
         } else {
+#if ZF_CONV_HI
+            convert_pair_hi(yE, cbE[k], crE[k], c0E, c1E, c2E, kk);
+            convert_pair_hi(yO, cbO[k], crO[k], c0O, c1O, c2O, kk);
+#else
             convert_pair(yE, cbE[k], crE[k], c0E, c1E, c2E);
             convert_pair(yO, cbO[k], crO[k], c0O, c1O, c2O);
+#endif
         }
-        const u32 rgE = prmt(c0E, c1E, 0x6240u);   // [R0 G0 R2 G2]
-        const u32 brO = prmt(c2E, c0O, 0x6240u);   // [B0 R1 B2 R3]
-        const u32 gbO = prmt(c1O, c2O, 0x6240u);   // [G1 B1 G3 B3]
+        const u32 rgE = prmt(c0E, c1E, sel);   // [R0 G0 R2 G2]
+        const u32 brO = prmt(c2E, c0O, sel);   // [B0 R1 B2 R3]
+        const u32 gbO = prmt(c1O, c2O, sel);   // [G1 B1 G3 B3]
         w[3 * k] = prmt(rgE, brO, 0x5410u);        // [R0 G0 B0 R1]
         w[3 * k + 1] = prmt(gbO, rgE, 0x7610u);    // [G1 B1 R2 G2]
         w[3 * k + 2] = prmt(brO, gbO, 0x7632u);    // [B2 R3 G3 B3]
@@ -1411,6 +1446,8 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const int tc = rtid;
     const int xu = tc % XU, rgA = tc / XU;                // this thread's units: (xu, rgA) and (xu, rgA + NRG/2)
     const bool ycc = im.out_kind == OUT_YCC;
+    u32 esel = (ZF_CONV_HI && !ycc) ? 0x7351u : 0x6240u, ekk = 0xC000C000u ^ ((u32)spc >> 30);   // (spc < 2^30: a constant ptxas cannot see)
+    asm volatile("" : "+r"(esel), "+r"(ekk));   // (opaque: kept in registers instead of being rematerialised in front of every use)
     int xs = X0 + 16 * xu;                                // first sample of the unit in the padded row
     // Where the unit's 48 bytes go (worker.rs:201-246): samples < n_norm ("normal" 16-sample chunks) sit at
     // byte 3*s, except bytes the tail chunk overwrites; the tail chunk (samples Wp-16..Wp-1) sits at T; the rest is never written
@@ -1588,7 +1625,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 if (y_base + yl < im.height) {
                     u32 yw[4];
                     load16(planes + yl * TWY + xl, FT::H == 2 || y16, yw);
-                    emit16(out + (size_t)(y_base + yl) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec);
+                    emit16(out + (size_t)(y_base + yl) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec, esel, ekk);
                 }
                 if (RPU == 2) {
 #pragma unroll
@@ -1601,12 +1638,12 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             if (y_base + yl0 < im.height) {
                 u32 yw[4];
                 load16(planes + yl0 * TWY + xl, FT::H == 2 || y16, yw);
-                emit16(out + (size_t)(y_base + yl0) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec);
+                emit16(out + (size_t)(y_base + yl0) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec, esel, ekk);
             }
             if (RPU == 2 && y_base + yl1 < im.height) {
                 u32 yw[4];
                 load16(planes + yl1 * TWY + xl, FT::H == 2 || y16, yw);
-                emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec);
+                emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec, esel, ekk);
             }
 #endif
         }
