@@ -146,6 +146,40 @@ ZJ_API int zj_batch_launches(const zj_batch *plan);
 ZJ_API uint64_t zj_batch_algorithmic_bytes(const zj_batch *plan);
 ZJ_API void zj_batch_destroy(zj_batch *plan);
 
+/* ---------------------------------------------------- device-side consumers */
+/* What a GPU consumer of the pixels reads, produced without leaving the device.  The reference's writers stop at
+ * interleaved u8 (the per-colourspace dispatch of src/worker.rs:113-133, stores of src/color_convert/scalar.rs:52-169);
+ * this descriptor extends them.  Every value is a function of the EXACT u8 the reference writes:
+ *   u8:            the byte itself; at half size (a + b + c + d + 2) >> 2 over the 2x2 box (odd last row / column dropped)
+ *   f32:           (float(u8) - mean[c]) * inv_std[c]    -- two IEEE fp32 operations (subtract, then multiply), no FMA;
+ *                  at half size the first operand is float(a + b + c + d) * 0.25f
+ *   f16:           the f32 value rounded to nearest even
+ * The default descriptor (zj_output_desc_default: HWC, u8, full size, all channels) is the reference's output unchanged. */
+typedef enum zj_layout { ZJ_LAYOUT_HWC = 0, ZJ_LAYOUT_CHW = 1 } zj_layout;
+typedef enum zj_dtype { ZJ_DTYPE_U8 = 0, ZJ_DTYPE_F16 = 1, ZJ_DTYPE_F32 = 2 } zj_dtype;
+typedef struct zj_output_desc {
+    uint32_t layout;      /* zj_layout                                                                          */
+    uint32_t dtype;       /* zj_dtype                                                                           */
+    uint32_t scale_log2;  /* 0 = full size, 1 = 2x2 box average to (width / 2) x (height / 2)                    */
+    uint32_t channels;    /* 0 = every byte of the colourspace's pixel; 3 = drop the 4th byte of RGBA / RGBX    */
+    float mean[4];        /* per channel, in u8 units (ignored for u8 output)                                   */
+    float inv_std[4];
+} zj_output_desc;
+ZJ_API void zj_output_desc_default(zj_output_desc *d);
+/* 1 when `d` asks for nothing but the reference's bytes */
+ZJ_API int zj_output_desc_is_default(const zj_output_desc *d);
+/* bytes / width / height / channels of image `img` under descriptor `d` (0 on a bad descriptor) */
+ZJ_API size_t zj_consumer_output_size(const zj_image *img, const zj_output_desc *d);
+ZJ_API int zj_consumer_output_shape(const zj_image *img, const zj_output_desc *d, uint32_t *out_w, uint32_t *out_h, uint32_t *out_c);
+/* The consumer alone: `src_dev` = width*height*nc interleaved u8 in device memory (nc = 1, 3 or 4) -> dst_dev.  Asynchronous on `stream`. */
+ZJ_API int zj_gpu_convert_device(int device, void *stream, const uint8_t *src_dev, uint32_t width, uint32_t height, uint32_t nc,
+                                 const zj_output_desc *d, void *dst_dev, size_t dst_len);
+/* zj_gpu_reconstruct_device followed by the consumer: out_dev[i] receives zj_consumer_output_size(&imgs[i], d) bytes.  The
+ * interleaved u8 intermediate lives in a stream-ordered scratch buffer and is produced and consumed sub-batch by sub-batch,
+ * sized to stay inside the L2 cache between the two kernels.  Returns after `stream` has drained. */
+ZJ_API int zj_gpu_reconstruct_device_ex(int device, void *stream, const zj_image *imgs, size_t n, const zj_output_desc *d,
+                                        void *const *out_dev, const size_t *out_len);
+
 /* Memory helpers so a non-CUDA host language can stage buffers without linking the CUDA runtime. */
 ZJ_API int zj_gpu_pinned_alloc(size_t bytes, void **p);
 ZJ_API int zj_gpu_pinned_free(void *p);
@@ -256,6 +290,12 @@ ZJ_API int zj_decode_batch_gpu(const zj_options *o, const uint8_t *const *bufs, 
  * that take the host route are uploaded after decoding.  The call returns when all pixels are in place. */
 ZJ_API int zj_decode_batch_gpu_device(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                                       uint8_t *const *out_dev, size_t *out_len, int *status, size_t *n_gpu_entropy);
+/* ... and handed to a device-side consumer (zj_output_desc above): out_dev[i] receives zj_consumer_output_size bytes in the
+ * layout / type / scale of `d` (sizes before decoding: zj_decoder_read_headers + zj_decoder_info give width, height and
+ * components; out_len[i] is checked).  On return out_len[i] = bytes written. */
+ZJ_API int zj_decode_batch_gpu_device_ex(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                                         const zj_output_desc *d, void *const *out_dev, size_t *out_len, int *status,
+                                         size_t *n_gpu_entropy);
 /* TEST-ONLY switches for three bugs of the reference's host stage that this library reproduces by default so that its
  * coefficient planes are the reference's.  A cleared bit makes the cited lines behave like libjpeg:
  *   Q9  src/huffman.rs:249-252   fast-AC entry `(k << 10) + ...` is an i16: |k| >= 32 loses its top bits

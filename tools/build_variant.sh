@@ -7,7 +7,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/zune-jpeg_b200/csrc
 out=$root/build/variants
 mkdir -p $out/obj_$name
-for f in zj_kernels.cu zj_capi.cu zj_entropy.cu zj_host_decoder.cpp; do
+for f in zj_kernels.cu zj_capi.cu zj_entropy.cu zj_consumer.cu zj_host_decoder.cpp; do
   o=$out/obj_$name/${f%.*}.o
   if [ $f = zj_kernels.cu ] || [ ! -f $o ] || [ $src/$f -nt $o ]; then
     rm -f $o
@@ -15,6 +15,6 @@ for f in zj_kernels.cu zj_capi.cu zj_entropy.cu zj_host_decoder.cpp; do
   fi
 done
 wait
-for f in zj_kernels zj_capi zj_entropy zj_host_decoder; do [ -f $out/obj_$name/$f.o ] || { echo "FAILED: $f"; exit 1; }; done
+for f in zj_kernels zj_capi zj_entropy zj_consumer zj_host_decoder; do [ -f $out/obj_$name/$f.o ] || { echo "FAILED: $f"; exit 1; }; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libzj_$name.so $out/obj_$name/*.o -cudart shared -lpthread
 echo built $out/libzj_$name.so

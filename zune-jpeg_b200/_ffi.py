@@ -45,6 +45,21 @@ class ZjImage(C.Structure):
     ]
 
 
+LAYOUT_HWC, LAYOUT_CHW = 0, 1
+DTYPE_U8, DTYPE_F16, DTYPE_F32 = 0, 1, 2
+
+
+class ZjOutputDesc(C.Structure):
+    _fields_ = [
+        ("layout", C.c_uint32),
+        ("dtype", C.c_uint32),
+        ("scale_log2", C.c_uint32),
+        ("channels", C.c_uint32),
+        ("mean", C.c_float * 4),
+        ("inv_std", C.c_float * 4),
+    ]
+
+
 class ZjOptions(C.Structure):
     _fields_ = [
         ("use_unsafe", C.c_uint32),
@@ -87,6 +102,14 @@ SYMBOLS = {
     "zj_batch_launches": (C.c_int, [_P]),
     "zj_batch_algorithmic_bytes": (C.c_uint64, [_P]),
     "zj_batch_destroy": (None, [_P]),
+    "zj_output_desc_default": (None, [C.POINTER(ZjOutputDesc)]),
+    "zj_output_desc_is_default": (C.c_int, [C.POINTER(ZjOutputDesc)]),
+    "zj_consumer_output_size": (C.c_size_t, [C.POINTER(ZjImage), C.POINTER(ZjOutputDesc)]),
+    "zj_consumer_output_shape": (C.c_int, [C.POINTER(ZjImage), C.POINTER(ZjOutputDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "zj_gpu_convert_device": (C.c_int, [C.c_int, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ZjOutputDesc), _P, C.c_size_t]),
+    "zj_gpu_reconstruct_device_ex": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, C.POINTER(ZjOutputDesc), _PP, C.POINTER(C.c_size_t)]),
+    "zj_decode_batch_gpu_device_ex": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(ZjOutputDesc),
+                                                C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "zj_gpu_pinned_alloc": (C.c_int, [C.c_size_t, _PP]),
     "zj_gpu_pinned_free": (C.c_int, [_P]),
     "zj_gpu_device_alloc": (C.c_int, [C.c_int, C.c_size_t, _PP]),

@@ -18,6 +18,7 @@
 
 namespace zj {
 cudaError_t launch_group(const DevImage *d_images, const LaunchGroup &g, cudaStream_t stream);
+cudaError_t launch_convert(const ConvImage *d_images, uint32_t count, uint32_t nc, uint32_t max_ow, uint32_t max_oh, const zj_output_desc &d, cudaStream_t s);
 }
 
 using namespace zj;
@@ -382,6 +383,164 @@ int zj_gpu_reconstruct_device(int device, void *stream, const zj_image *imgs, si
     // the descriptor array must outlive the kernels
     if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize"); }
     zj_batch_destroy(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- device-side consumers
+void zj_output_desc_default(zj_output_desc *d)
+{
+    if (!d) return;
+    memset(d, 0, sizeof(*d));
+    for (int c = 0; c < 4; c++) d->inv_std[c] = 1.0f;
+}
+
+static int desc_check(const zj_output_desc *d)
+{
+    if (!d || d->layout > ZJ_LAYOUT_CHW || d->dtype > ZJ_DTYPE_F32 || d->scale_log2 > 1 || (d->channels != 0 && d->channels != 3)) return ZJ_ERR_INVALID_ARG;
+    return ZJ_OK;
+}
+
+int zj_output_desc_is_default(const zj_output_desc *d)
+{
+    return d && d->layout == ZJ_LAYOUT_HWC && d->dtype == ZJ_DTYPE_U8 && d->scale_log2 == 0 && d->channels == 0;
+}
+
+static size_t dtype_size(uint32_t dt) { return dt == ZJ_DTYPE_U8 ? 1 : (dt == ZJ_DTYPE_F16 ? 2 : 4); }
+
+static int conv_shape(uint32_t width, uint32_t height, uint32_t nc, const zj_output_desc *d, uint32_t *ow, uint32_t *oh, uint32_t *oc)
+{
+    int rc = desc_check(d);
+    if (rc) return rc;
+    if (nc != 1 && nc != 3 && nc != 4) return ZJ_ERR_INVALID_ARG;
+    *ow = width >> d->scale_log2;
+    *oh = height >> d->scale_log2;
+    *oc = (d->channels == 3 && nc == 4) ? 3u : nc;
+    return ZJ_OK;
+}
+
+int zj_consumer_output_shape(const zj_image *img, const zj_output_desc *d, uint32_t *out_w, uint32_t *out_h, uint32_t *out_c)
+{
+    if (!img || !out_w || !out_h || !out_c) return ZJ_ERR_INVALID_ARG;
+    return conv_shape(img->width, img->height, (uint32_t)num_components(img->out_cs), d, out_w, out_h, out_c);
+}
+
+size_t zj_consumer_output_size(const zj_image *img, const zj_output_desc *d)
+{
+    uint32_t ow, oh, oc;
+    if (!img || zj_output_size(img) == 0 || zj_consumer_output_shape(img, d, &ow, &oh, &oc) != ZJ_OK) return 0;
+    return (size_t)ow * oh * oc * dtype_size(d->dtype);
+}
+
+int zj_gpu_convert_device(int device, void *stream, const uint8_t *src_dev, uint32_t width, uint32_t height, uint32_t nc,
+                          const zj_output_desc *d, void *dst_dev, size_t dst_len)
+{
+    ConvImage ci{};
+    int rc = conv_shape(width, height, nc, d, &ci.ow, &ci.oh, &ci.oc);
+    if (rc) return rc;
+    if (!src_dev || !dst_dev) return ZJ_ERR_INVALID_ARG;
+    if (dst_len < (size_t)ci.ow * ci.oh * ci.oc * dtype_size(d->dtype)) return ZJ_ERR_SHORT_OUTPUT;
+    rc = set_device(device);
+    if (rc) return rc;
+    if (ci.ow == 0 || ci.oh == 0) return ZJ_OK;
+    ci.src = src_dev; ci.dst = dst_dev; ci.width = width; ci.height = height; ci.nc = nc;
+    cudaStream_t s = (cudaStream_t)stream;
+    ConvImage *d_ci = nullptr;
+    CU(cudaMallocAsync((void **)&d_ci, sizeof(ci), s));
+    cudaError_t e = cudaMemcpyAsync(d_ci, &ci, sizeof(ci), cudaMemcpyHostToDevice, s);   // (pageable source: staged before the call returns)
+    if (e == cudaSuccess) { e = launch_convert(d_ci, 1, nc, ci.ow, ci.oh, *d, s); g_launches.fetch_add(1); }
+    cudaFreeAsync(d_ci, s);
+    if (e != cudaSuccess) return cuda_fail(e, "zj_gpu_convert_device");
+    return ZJ_OK;
+}
+
+// Sub-batch budget of the u8 intermediate: what the reconstruction kernel writes should still be in the 126 MB L2 when the
+// consumer kernel reads it (the coefficient planes stream through the same cache, hence well below its size).
+static size_t consumer_chunk_bytes()
+{
+    static const size_t v = [] {
+        const char *e = getenv("ZJ_CONSUMER_CHUNK_MB");
+        long mb = e ? atol(e) : 48;
+        if (mb < 1) mb = 1;
+        return (size_t)mb << 20;
+    }();
+    return v;
+}
+
+int zj_gpu_reconstruct_device_ex(int device, void *stream, const zj_image *imgs, size_t n, const zj_output_desc *d,
+                                 void *const *out_dev, const size_t *out_len)
+{
+    int rc = desc_check(d);
+    if (rc) return rc;
+    if (zj_output_desc_is_default(d)) return zj_gpu_reconstruct_device(device, stream, imgs, n, reinterpret_cast<uint8_t *const *>(out_dev), out_len);
+    if ((!imgs || !out_dev || !out_len) && n) return ZJ_ERR_INVALID_ARG;
+    rc = set_device(device);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    // geometry, sizes, sub-batches of consecutive images
+    std::vector<ConvImage> conv(n);
+    std::vector<size_t> u8_size(n), u8_off(n);
+    struct Chunk { size_t first, count, bytes; };
+    std::vector<Chunk> chunks;
+    size_t scratch_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        u8_size[i] = zj_output_size(&imgs[i]);
+        if (u8_size[i] == 0) { rc = zj_validate_image(&imgs[i]); return rc ? rc : (int)ZJ_ERR_INVALID_ARG; }
+        ConvImage &ci = conv[i];
+        ci.width = imgs[i].width; ci.height = imgs[i].height; ci.nc = (uint32_t)num_components(imgs[i].out_cs);
+        rc = conv_shape(ci.width, ci.height, ci.nc, d, &ci.ow, &ci.oh, &ci.oc);
+        if (rc) return rc;
+        if (!out_dev[i]) return ZJ_ERR_INVALID_ARG;
+        if (out_len[i] < (size_t)ci.ow * ci.oh * ci.oc * dtype_size(d->dtype)) return ZJ_ERR_SHORT_OUTPUT;
+        ci.dst = out_dev[i];
+        const size_t padded = (u8_size[i] + 255) & ~(size_t)255;
+        if (chunks.empty() || chunks.back().bytes + padded > consumer_chunk_bytes()) chunks.push_back({i, 0, 0});
+        u8_off[i] = chunks.back().bytes;
+        chunks.back().bytes += padded;
+        chunks.back().count++;
+        scratch_bytes = std::max(scratch_bytes, chunks.back().bytes);
+    }
+    if (n == 0) return ZJ_OK;
+    uint8_t *scratch = nullptr;
+    ConvImage *d_conv = nullptr;
+    CU(cudaMallocAsync((void **)&scratch, scratch_bytes, s));
+    cudaError_t e = cudaMallocAsync((void **)&d_conv, n * sizeof(ConvImage), s);
+    if (e != cudaSuccess) { cudaFreeAsync(scratch, s); return cuda_fail(e, "cudaMallocAsync(consumer descriptors)"); }
+    for (size_t i = 0; i < n; i++) conv[i].src = scratch + u8_off[i];
+    e = cudaMemcpyAsync(d_conv, conv.data(), n * sizeof(ConvImage), cudaMemcpyHostToDevice, s);
+    std::vector<zj_batch *> batches;
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(consumer descriptors)");
+    for (size_t c = 0; c < chunks.size() && rc == ZJ_OK; c++) {
+        const Chunk &ch = chunks[c];
+        std::vector<uint8_t *> outs(ch.count);
+        std::vector<size_t> lens(ch.count);
+        for (size_t k = 0; k < ch.count; k++) { outs[k] = scratch + u8_off[ch.first + k]; lens[k] = u8_size[ch.first + k]; }
+        zj_batch *b = nullptr;
+        rc = batch_create_impl(device, imgs + ch.first, ch.count, outs.data(), lens.data(), &b, true, s);
+        if (rc) break;
+        batches.push_back(b);
+        rc = zj_batch_run(b, s);
+        // one consumer launch per run of images with the same number of source bytes per pixel
+        for (size_t k = 0; k < ch.count && rc == ZJ_OK;) {
+            size_t k1 = k;
+            uint32_t mw = 0, mh = 0;
+            while (k1 < ch.count && conv[ch.first + k1].nc == conv[ch.first + k].nc) {
+                mw = std::max(mw, conv[ch.first + k1].ow); mh = std::max(mh, conv[ch.first + k1].oh);
+                k1++;
+            }
+            if (mw && mh) {
+                e = launch_convert(d_conv + ch.first + k, (uint32_t)(k1 - k), conv[ch.first + k].nc, mw, mh, *d, s);
+                g_launches.fetch_add(1);
+                if (e != cudaSuccess) rc = cuda_fail(e, "consumer launch");
+            }
+            k = k1;
+        }
+    }
+    // the descriptor arrays and the scratch must outlive the kernels
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && rc == ZJ_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    for (zj_batch *b : batches) zj_batch_destroy(b);
+    cudaFreeAsync(d_conv, s);
+    cudaFreeAsync(scratch, s);
     return rc;
 }
 

@@ -80,4 +80,12 @@ struct LaunchGroup {
     uint32_t max_tiles, max_strips;
 };
 
+// One image of a consumer launch (zj_consumer.cu): interleaved u8 pixels in, the layout / type / scale of zj_output_desc out.
+struct ConvImage {
+    const uint8_t *src;           // u8, interleaved, width * height * nc
+    void *dst;
+    uint32_t width, height, nc;   // source geometry
+    uint32_t ow, oh, oc;          // output geometry (oc = channels written)
+};
+
 }  // namespace zj

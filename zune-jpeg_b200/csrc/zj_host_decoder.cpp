@@ -1892,6 +1892,65 @@ ZJ_API int zj_decode_batch_gpu_device(const zj_options *o, const uint8_t *const 
     return decode_batch_gpu_impl(o, bufs, lens, n, const_cast<uint8_t **>(out_dev), out_len, status, n_gpu_entropy, true);
 }
 
+// The device-output call with a consumer descriptor: the pixels are reconstructed into a stream-ordered u8 scratch buffer and
+// converted from there (zj_consumer.cu); with the default descriptor this IS zj_decode_batch_gpu_device.
+ZJ_API int zj_decode_batch_gpu_device_ex(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                                         const zj_output_desc *d, void *const *out_dev, size_t *out_len, int *status,
+                                         size_t *n_gpu_entropy)
+{
+    if (!d) return ZJ_ERR_INVALID_ARG;
+    if (zj_output_desc_is_default(d))
+        return zj_decode_batch_gpu_device(o, bufs, lens, n, reinterpret_cast<uint8_t *const *>(out_dev), out_len, status, n_gpu_entropy);
+    if ((!bufs || !lens || !out_dev || !out_len || !status) && n) return ZJ_ERR_INVALID_ARG;
+    zj_options opt;
+    if (o) opt = *o; else zj_options_default(&opt);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= opt.device) { cudaGetLastError(); return ZJ_ERR_NO_DEVICE; }
+    if (cudaSetDevice(opt.device) != cudaSuccess) { cudaGetLastError(); return ZJ_ERR_NO_DEVICE; }
+    // geometry of every image from its headers: the u8 intermediate and the caller's buffers are sized before decoding
+    struct Geo { uint32_t w = 0, h = 0, nc = 0; size_t u8 = 0, off = 0; bool ok = false; };
+    std::vector<Geo> geo(n);
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        zj_decoder *dd = zj_decoder_new(&opt);
+        zj_image_info info;
+        if (dd && zj_decoder_read_headers(dd, bufs[i], lens[i]) == ZJ_OK && zj_decoder_info(dd, &info) == ZJ_OK && info.valid) {
+            Geo &g = geo[i];
+            g.w = info.width; g.h = info.height;
+            const uint32_t cs = zj_decoder_out_colorspace(dd);
+            g.nc = cs == ZJ_CS_GRAYSCALE ? 1u : ((cs == ZJ_CS_RGB || cs == ZJ_CS_YCBCR) ? 3u : 4u);
+            g.u8 = (size_t)g.w * g.h * g.nc;
+            g.off = total;
+            total += (g.u8 + 255) & ~(size_t)255;
+            g.ok = true;
+        }
+        if (dd) zj_decoder_free(dd);
+    }
+    uint8_t *scratch = nullptr;
+    if (total && cudaMalloc(&scratch, total) != cudaSuccess) { cudaGetLastError(); return ZJ_ERR_OOM; }
+    std::vector<uint8_t *> mid(n);
+    std::vector<size_t> mid_len(n);
+    // (images whose headers do not parse get a dummy one-byte slot: the decode call reports their error)
+    for (size_t i = 0; i < n; i++) { mid[i] = geo[i].ok ? scratch + geo[i].off : scratch; mid_len[i] = geo[i].ok ? geo[i].u8 : 0; }
+    int rc = zj_decode_batch_gpu_device(&opt, bufs, lens, n, mid.data(), mid_len.data(), status, n_gpu_entropy);
+    int failed = rc;
+    if (rc >= 0) {
+        for (size_t i = 0; i < n; i++) {
+            if (status[i] != ZJ_OK) { out_len[i] = 0; continue; }
+            const Geo &g = geo[i];
+            const size_t have = out_len[i];
+            const size_t es = d->dtype == ZJ_DTYPE_U8 ? 1 : (d->dtype == ZJ_DTYPE_F16 ? 2 : 4);
+            const size_t need = (size_t)(g.w >> d->scale_log2) * (g.h >> d->scale_log2) * ((d->channels == 3 && g.nc == 4) ? 3 : g.nc) * es;
+            int st = zj_gpu_convert_device(opt.device, nullptr, mid[i], g.w, g.h, g.nc, d, out_dev[i], have);
+            if (st != ZJ_OK) { status[i] = st; failed++; out_len[i] = 0; }
+            else out_len[i] = need;
+        }
+        if (cudaStreamSynchronize(nullptr) != cudaSuccess) { cudaGetLastError(); failed = ZJ_ERR_CUDA; }
+    }
+    if (scratch) cudaFree(scratch);
+    return failed;
+}
+
 ZJ_API void zj_host_set_quirks(uint32_t mask) { g_quirks.store(mask & ZJ_QUIRK_ALL); }
 ZJ_API uint32_t zj_host_get_quirks(void) { return g_quirks.load(); }
 ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d) { return d ? d->last_entropy_segments : 0; }

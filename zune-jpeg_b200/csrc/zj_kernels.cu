@@ -361,42 +361,56 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
     }
 }
 
-#ifndef ZF_RP_UNROLL
-#define ZF_RP_UNROLL 1
+#ifndef ZF_UNROLL_HV
+#define ZF_UNROLL_HV 1
 #endif
-#define ZF_PRAGMA(x) _Pragma(#x)
-#define ZF_UNROLL(n) ZF_PRAGMA(unroll n)
-template <typename AfterRows>
+#ifndef ZF_UNROLL_V
+#define ZF_UNROLL_V 1
+#endif
+#ifndef ZF_UNROLL_H
+#define ZF_UNROLL_H 4
+#endif
+#ifndef ZF_UNROLL_NONE
+#define ZF_UNROLL_NONE 4
+#endif
+#ifndef ZF_UNROLL_GRAY
+#define ZF_UNROLL_GRAY 4
+#endif
+// UNROLL: 1 = the row-pair loop stays rolled (4:2:0 / 4:4:0: the consumers' hot code leaves no room in the 32 KB instruction
+// cache for more); 4 = unrolled (everything that depends on the row pair becomes static: +7 % on 4:2:2, +10 % luma-only)
+template <int UNROLL, typename AfterRows>
 __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, const u32 sc, const u32 *__restrict__ qtw, uint8_t *__restrict__ dst, const int dst_stride,
                                             AfterRows after_rows)
 {
     constexpr u32 CH = 16u * ZF_PRODUCERS;
-    u32 acc = 0, dcmask = 0xffff0000u, dc0 = 0;
-    bool rows45 = false, rows67 = false;       // warp-uniform: anything in rows 4-5 / 6-7 of any block of the warp
-    ZF_UNROLL(ZF_RP_UNROLL)
-    for (int rp = 0; rp < 4; rp++) {          // rows 2rp, 2rp+1
+    // Row pairs are visited from the bottom (rows 6-7) to the top (rows 0-1): the first word of the LAST visited pair is then
+    // the one that holds the DC coefficient and is simply what `carry` is left with -- no per-iteration selects.  acc collects
+    // everything except that word's low half (all 63 AC coefficients); nz collects, one bit per pair, which pairs were
+    // transformed (warp-uniform: bit 3 = rows 6-7 ... bit 0 = rows 0-1).
+    u32 acc = 0, carry = 0, nz = 0;
+#pragma unroll UNROLL
+    for (int i = 96; i >= 0; i -= 32) {        // i = 32 * row pair: byte offset in the slot and in the table, 1/256 of the scratch offset
         u32 a0, a1, a2, a3, b0, b1, b2, b3;
-        const u32 pa = sl ^ (u32)(rp << 5);
+        const u32 pa = sl ^ (u32)i;
         lds128(pa, a0, a1, a2, a3);
         lds128(pa ^ 16u, b0, b1, b2, b3);
-        if (rp == 0) dc0 = a0;
-        const u32 hi = a2 | a3 | b2 | b3, all = a0 | a1 | b0 | b1 | hi;
-        acc |= (a0 & dcmask) | a1 | b0 | b1 | hi;
-        dcmask = 0xffffffffu;
-        const u32 o = sc + (u32)(rp * 4) * CH;
+        const u32 hi = a2 | a3 | b2 | b3, rest = a1 | b0 | b1 | hi;
+        acc |= carry | rest;
+        carry = a0;
+        nz <<= 1;
+        const u32 o = sc + (u32)i * (CH / 8u);
         // the pair is skipped when it is zero in every block of the warp (a zero row transforms to exact zeros) ...
-        if (!__any_sync(0xffffffffu, all != 0)) {
-            if (rp < 2) {                      // (rows 4-7: zeroed below, and only if the column pass will read them)
+        if (!__any_sync(0xffffffffu, (a0 | rest) != 0)) {
+            if (i < 64) {                      // (rows 4-7: zeroed below, and only if the column pass will read them)
 #pragma unroll
                 for (int k = 0; k < 4; k++) sts128(o + (u32)k * CH, 0u, 0u, 0u, 0u);
             }
             continue;
         }
-        if (rp == 2) rows45 = true;
-        if (rp == 3) rows67 = true;
+        nz |= 1u;
         // ... and uses the 4-input form when nothing sits in columns 4-7
         const bool anyhi = __any_sync(0xffffffffu, hi != 0);
-        const uint4 qa = *reinterpret_cast<const uint4 *>(qtw + rp * 8), qb = *reinterpret_cast<const uint4 *>(qtw + rp * 8 + 4);
+        const uint4 qa = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(qtw) + i), qb = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(qtw) + i + 16);
         u32 s0 = dp2a_lo(a0, qa.x), s1 = dp2a_hi(a0, qa.x), s2 = dp2a_lo(a1, qa.y), s3 = dp2a_hi(a1, qa.y), s4 = 0, s5 = 0, s6 = 0, s7 = 0;
         u32 t0 = dp2a_lo(b0, qb.x), t1 = dp2a_hi(b0, qb.x), t2 = dp2a_lo(b1, qb.y), t3 = dp2a_hi(b1, qb.y), t4 = 0, t5 = 0, t6 = 0, t7 = 0;
         if (anyhi) {
@@ -413,6 +427,9 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
         sts128(o + 2 * CH, t0, t1, t2, t3);
         sts128(o + 3 * CH, t4, t5, t6, t7);
     }
+    acc |= carry & 0xffff0000u;
+    const u32 dc0 = carry;
+    const bool rows45 = (nz & 4u) != 0, rows67 = (nz & 8u) != 0;
     const bool rows47 = rows45 || rows67;
     if (rows47 && !(rows45 && rows67)) {       // the 8-input column pass reads rows 4-7: zero the pair that was skipped
         const u32 o = sc + (u32)(rows45 ? 12 : 8) * CH;
@@ -1121,6 +1138,8 @@ template <int MODE> struct FastTraits {
     static constexpr int YB = TWY / 8, CB = TWC / 8;  // blocks per block row of the tile
     static constexpr int CS = TWC + 24;               // chroma smem row: left halo | tile | right halo | special
     static constexpr int NSLOT = MODE == MODE_H ? 2 : (MODE == MODE_HV ? 3 : 0);  // halo block columns per chroma plane
+    // row-pair loop of the IDCT: unrolled where the instruction cache has room for it (measured per mode)
+    static constexpr int IDCT_UNROLL = MODE == MODE_HV ? ZF_UNROLL_HV : (MODE == MODE_V ? ZF_UNROLL_V : (MODE == MODE_H ? ZF_UNROLL_H : ZF_UNROLL_NONE));
     static constexpr int NY = YBR * YB, NC = CBR * CB, PER = NC + NSLOT * CBR;
     static constexpr int YBYTES = ROWS * TWY, CBYTES = CROWS * CS, BUF = YBYTES + 2 * CBYTES;  // one buffer of sample planes
     static_assert(NY + 2 * PER <= 2 * ZF_PRODUCERS, "two 8x8 blocks per producer thread");
@@ -1433,7 +1452,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     issue(ps, ps ? qa0 : qa1, ps ? qb0 : qb1, ps ? (it + 1 < n_it ? jm0 : 0u) : jm1);
                     if (ps) { qa0 += st0; qb0 += st0; } else { qa1 += st1; qb1 += st1; }
                 };
-                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
+                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled<FT::IDCT_UNROLL>(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
                 else refill();
             }
             bar_arrive(BAR_FULL + buf);
@@ -1837,7 +1856,7 @@ gray_fast_kernel(const DevImage *__restrict__ images, const int spc)
             auto refill = [&]() {
                 if (it + 1 < n_it) { issue(q0, row_exists(it + 1)); q0 += step; }
             };
-            if (work && row_exists(it)) idct_rolled(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, refill);
+            if (work && row_exists(it)) idct_rolled<ZF_UNROLL_GRAY>(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, refill);
             else refill();
             bar_arrive(BAR_FULL + (it & 1));
         }

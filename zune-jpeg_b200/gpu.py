@@ -198,3 +198,109 @@ class Event:
         ms = C.c_float()
         _check(_ffi.load().zj_gpu_event_elapsed_ms(self.device, self.ptr, stop.ptr, C.byref(ms)), "event_elapsed")
         return float(ms.value)
+
+
+# ------------------------------------------------------------------ device-side consumers
+_NP_DTYPES = {_ffi.DTYPE_U8: np.uint8, _ffi.DTYPE_F16: np.float16, _ffi.DTYPE_F32: np.float32}
+_TYPESTR = {_ffi.DTYPE_U8: "|u1", _ffi.DTYPE_F16: "<f2", _ffi.DTYPE_F32: "<f4"}
+
+
+class OutputDesc:
+    """zj_output_desc: layout 'HWC' | 'CHW', dtype 'u8' | 'f16' | 'f32', half = 2x2 box down-scale, channels 0 (all) | 3,
+    per-channel mean / inv_std in u8 units.  Float values are (float(u8) - mean) * inv_std of the reference's exact bytes."""
+
+    def __init__(self, layout: str = "HWC", dtype: str = "u8", half: bool = False, channels: int = 0,
+                 mean=(0.0, 0.0, 0.0, 0.0), inv_std=(1.0, 1.0, 1.0, 1.0)):
+        d = _ffi.ZjOutputDesc()
+        d.layout = {"HWC": _ffi.LAYOUT_HWC, "CHW": _ffi.LAYOUT_CHW}[layout]
+        d.dtype = {"u8": _ffi.DTYPE_U8, "f16": _ffi.DTYPE_F16, "f32": _ffi.DTYPE_F32}[dtype]
+        d.scale_log2 = 1 if half else 0
+        d.channels = channels
+        mean, inv_std = list(mean) + [0.0] * 4, list(inv_std) + [1.0] * 4
+        for c in range(4):
+            d.mean[c], d.inv_std[c] = float(mean[c]), float(inv_std[c])
+        self.c = d
+
+    @property
+    def chw(self) -> bool:
+        return self.c.layout == _ffi.LAYOUT_CHW
+
+    @property
+    def np_dtype(self):
+        return _NP_DTYPES[self.c.dtype]
+
+    def shape_of(self, img: ZjImage):
+        w, h, ch = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(_ffi.load().zj_consumer_output_shape(C.byref(img), C.byref(self.c), C.byref(w), C.byref(h), C.byref(ch)), "zj_consumer_output_shape")
+        return (ch.value, h.value, w.value) if self.chw else (h.value, w.value, ch.value)
+
+    def expected(self, u8: np.ndarray, width: int, height: int, nc: int) -> np.ndarray:
+        """The specification, applied to the reference's bytes with numpy (tests: `u8` comes from the oracle)."""
+        a = np.asarray(u8, np.uint8).reshape(height, width, nc)
+        oc = 3 if (self.c.channels == 3 and nc == 4) else nc
+        a = a[:, :, :oc]
+        mean = np.array(list(self.c.mean)[:oc], np.float32)
+        inv = np.array(list(self.c.inv_std)[:oc], np.float32)
+        if self.c.scale_log2:
+            h2, w2 = height // 2, width // 2
+            s = a[: 2 * h2, : 2 * w2].astype(np.uint32).reshape(h2, 2, w2, 2, oc).sum(axis=(1, 3))
+            r = ((s + 2) >> 2).astype(np.uint8) if self.c.dtype == _ffi.DTYPE_U8 else ((s.astype(np.float32) * np.float32(0.25) - mean) * inv)
+        else:
+            r = a if self.c.dtype == _ffi.DTYPE_U8 else ((a.astype(np.float32) - mean) * inv)
+        r = r.astype(self.np_dtype)
+        return np.ascontiguousarray(r.transpose(2, 0, 1)) if self.chw else np.ascontiguousarray(r)
+
+
+class DeviceArray:
+    """A typed view of device memory produced by the consumer kernels.  Exposes ``__cuda_array_interface__`` (version 3), so
+    ``torch.as_tensor(a, device='cuda')``, ``cupy.asarray(a)`` and numba read it in place; ``__dlpack__`` goes through torch."""
+
+    def __init__(self, buf: DeviceBuffer, shape, dtype_code: int):
+        self.buf, self.shape, self.dtype_code = buf, tuple(int(x) for x in shape), dtype_code
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": _TYPESTR[self.dtype_code], "data": (int(self.buf.ptr or 0), False), "version": 3, "strides": None}
+
+    def to_torch(self):
+        import torch
+        return torch.as_tensor(self, device=f"cuda:{self.buf.device}")
+
+    def __dlpack__(self, stream=None):
+        return self.to_torch().__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+        return (2, self.buf.device)   # kDLCUDA
+
+    def download(self) -> np.ndarray:
+        n = int(np.prod(self.shape)) * np.dtype(_NP_DTYPES[self.dtype_code]).itemsize
+        return self.buf.download(n).view(_NP_DTYPES[self.dtype_code]).reshape(self.shape)
+
+
+def reconstruct_device_ex(images, desc: OutputDesc, device: int = 0, stream=None):
+    """zj_gpu_reconstruct_device_ex: `images` carry DEVICE coefficient planes; returns one DeviceArray per image."""
+    lib = _ffi.load()
+    n = len(images)
+    arr = _img_array(images)
+    outs, ptrs, lens = [], (C.c_void_p * n)(), (C.c_size_t * n)()
+    for i, im in enumerate(images):
+        sz = int(lib.zj_consumer_output_size(C.byref(im), C.byref(desc.c)))
+        if sz == 0 and output_size(im) == 0:
+            _check(validate(im) or _ffi.ERR_INVALID_ARG, "zj_validate_image")
+        b = DeviceBuffer(max(sz, 1), device)
+        outs.append(DeviceArray(b, desc.shape_of(im), desc.c.dtype))
+        ptrs[i], lens[i] = b.ptr, sz
+    _check(lib.zj_gpu_reconstruct_device_ex(device, stream, arr, n, C.byref(desc.c), ptrs, lens), "zj_gpu_reconstruct_device_ex")
+    return outs
+
+
+def convert_device(src: DeviceBuffer, width: int, height: int, nc: int, desc: OutputDesc, device: int = 0, stream=None) -> DeviceArray:
+    """zj_gpu_convert_device: the consumer alone over interleaved u8 pixels already in device memory."""
+    lib = _ffi.load()
+    ow, oh = width >> desc.c.scale_log2, height >> desc.c.scale_log2
+    oc = 3 if (desc.c.channels == 3 and nc == 4) else nc
+    sz = ow * oh * oc * np.dtype(desc.np_dtype).itemsize
+    b = DeviceBuffer(max(sz, 1), device)
+    _check(lib.zj_gpu_convert_device(device, stream, src.ptr, width, height, nc, C.byref(desc.c), b.ptr, sz), "zj_gpu_convert_device")
+    synchronize(device, stream)
+    return DeviceArray(b, (oc, oh, ow) if desc.chw else (oh, ow, oc), desc.c.dtype)
