@@ -277,6 +277,13 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
 /* zj_decode_batch keeps its workers' decoders (pinned coefficient planes sized for the largest image seen, two per host
  * thread) for the next call; this frees them. */
 ZJ_API void zj_release_host_caches(void);
+/* Device-side state kept between calls, and its release.  zj_gpu_reconstruct[_submit] keeps, per host thread that called it,
+ * its staging streams and up to three device staging buffers (256 MB sub-batches by default); zj_decode_batch_gpu[_device]
+ * keeps two slots of device staging memory (>= 1 GB each once used; a slot that a call grew beyond ZJ_RETAIN_MB megabytes,
+ * default 1024, is freed when that call ends), their streams and small pinned blocks.  zj_release_device_caches frees all of
+ * it except what a thread is using at that moment (it waits for a zj_decode_batch_gpu call in flight); the next call
+ * allocates again.  Call it when the process wants its HBM back, e.g. a data loader that shares the GPU with a training job. */
+ZJ_API void zj_release_device_caches(void);
 /* The same call with the entropy stage on the GPU too, for the JPEGs that allow it: baseline scans with restart markers (DRI)
  * whose every interval ends the way the reference's sequential loop (src/mcu.rs:253-351, 386-418) ends it.  Their files are
  * uploaded instead of their coefficient planes, one GPU thread per restart interval runs the reference's bit reader and MCU

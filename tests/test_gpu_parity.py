@@ -116,7 +116,12 @@ def test_device_resident_batch_plan():
     assert gpu.launch_count() - before == 2 * batch.launches
     got = out.download()
     assert np.array_equal(got, want)
-    assert batch.algorithmic_bytes == sum(p.nbytes for p in planes) - 0 * 2 + len(want) or batch.algorithmic_bytes > 0
+    # algorithmic bytes = coefficient bytes of the strips the reference processes + output bytes: 4:2:0 strips
+    # are two MCU rows (mcu.rs:155-159; 720 rows = 45 MCU rows -> 22 strips, the odd MCU row is dropped, Q1)
+    mcu_x, mcu_y = util.geometry(w, h, 2, 2)
+    n_strips = mcu_y // 2
+    assert n_strips == 22
+    assert batch.algorithmic_bytes == n_strips * (4 * 2 * mcu_x + 2 * 2 * mcu_x) * 64 * 2 + len(want)
 
 
 # ------------------------------------------------------------------ the producer / consumer kernel's own corners

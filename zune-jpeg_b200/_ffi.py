@@ -143,6 +143,7 @@ SYMBOLS = {
     "zj_decode_batch_gpu_device": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
                                              C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "zj_release_host_caches": (None, []),
+    "zj_release_device_caches": (None, []),
     "zj_host_set_quirks": (None, [C.c_uint32]),
     "zj_host_get_quirks": (C.c_uint32, []),
     "zj_decoder_entropy_segments": (C.c_size_t, [_P]),

@@ -544,6 +544,51 @@ int zj_gpu_reconstruct_device_ex(int device, void *stream, const zj_image *imgs,
     return rc;
 }
 
+// Staging state of zj_gpu_reconstruct_submit, leased per host thread (see there); the idle ones are what
+// zj_release_device_caches frees.
+constexpr int ZJ_NS_MAX = 4;
+struct StreamCache {
+    cudaStream_t s[64][ZJ_NS_MAX] = {};
+    uint8_t *buf[64][ZJ_NS_MAX] = {};
+    size_t cap[64][ZJ_NS_MAX] = {};
+    cudaEvent_t ev[64][ZJ_NS_MAX][3] = {};   // per staging buffer: planes uploaded / kernels done / pixels downloaded
+    bool ev_rec[64][ZJ_NS_MAX] = {};
+};
+struct CachePool {
+    std::mutex mu;
+    std::vector<StreamCache *> idle;
+};
+static CachePool g_stream_pool;
+
+// frees the streams, events and device staging buffers of every cache no thread holds (hidden symbol; the exported entry
+// point is zj_release_device_caches in zj_host_decoder.cpp)
+extern "C" void zj_capi_release_stream_caches(void)
+{
+    std::vector<StreamCache *> drop;
+    {
+        std::lock_guard<std::mutex> lock(g_stream_pool.mu);
+        drop.swap(g_stream_pool.idle);
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (StreamCache *c : drop) {
+        for (int dev = 0; dev < 64; dev++) {
+            bool any = false;
+            for (int k = 0; k < ZJ_NS_MAX; k++) any = any || c->s[dev][k] || c->buf[dev][k];
+            if (!any || cudaSetDevice(dev) != cudaSuccess) continue;
+            for (int k = 0; k < ZJ_NS_MAX; k++) {
+                if (c->s[dev][k]) cudaStreamSynchronize(c->s[dev][k]);
+                if (c->buf[dev][k]) cudaFree(c->buf[dev][k]);
+                for (int e = 0; e < 3; e++) if (c->ev[dev][k][e]) cudaEventDestroy(c->ev[dev][k][e]);
+                if (c->s[dev][k]) cudaStreamDestroy(c->s[dev][k]);
+            }
+        }
+        delete c;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+}
+
 // Host entry point: stage planes H2D, run, copy pixels D2H.  Images are processed in sub-batches on internal streams so
 // that the copies of one sub-batch overlap the kernels of the other.  Split in two halves: zj_gpu_reconstruct_submit queues
 // everything and returns while the GPU works (the caller's planes and outputs stay in use), zj_gpu_reconstruct_finish waits
@@ -568,7 +613,9 @@ int zj_gpu_reconstruct_finish(zj_pending *p)
     }
     for (int k = 0; k < p->ns; k++) if (p->done[k]) cudaEventDestroy(p->done[k]);
     for (zj_batch *b : p->batches) zj_batch_destroy(b);
-    if (rc == ZJ_OK) { cudaError_t e = cudaStreamSynchronize(p->user); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(user)"); }
+    // (user == NULL is the legacy default stream: synchronising it would serialise this thread against every blocking stream
+    // of the process, and nothing of this call was queued on it -- the internal streams were waited for above)
+    if (rc == ZJ_OK && p->user) { cudaError_t e = cudaStreamSynchronize(p->user); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(user)"); }
     delete p;
     return rc;
 }
@@ -600,33 +647,19 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
     // ... and so is the device staging buffer of every stream (grown on demand, reused in stream order): memory that the
     // stream-ordered pool hands from one stream to another makes the second stream wait for the first one's work, which
     // serialises the upload of one sub-batch behind the download of the previous one
-    struct StreamCache {
-        cudaStream_t s[64][NS_MAX] = {};
-        uint8_t *buf[64][NS_MAX] = {};
-        size_t cap[64][NS_MAX] = {};
-        cudaEvent_t ev[64][NS_MAX][3] = {};   // per staging buffer: planes uploaded / kernels done / pixels downloaded
-        bool ev_rec[64][NS_MAX] = {};
-    };
-    // A thread leases a cache for its lifetime and hands it back when it exits (zj_decode_batch starts fresh worker threads
-    // in every call: a plain thread_local would strand its streams and device buffers with every one of them).
-    struct CachePool {
-        std::mutex mu;
-        std::vector<StreamCache *> idle;
-    };
-    static CachePool pool;
     struct Lease {
         StreamCache *c = nullptr;
         ~Lease()
         {
             if (!c) return;
-            std::lock_guard<std::mutex> lock(pool.mu);
-            pool.idle.push_back(c);
+            std::lock_guard<std::mutex> lock(g_stream_pool.mu);
+            g_stream_pool.idle.push_back(c);
         }
     };
     thread_local Lease lease;
     if (!lease.c) {
-        std::lock_guard<std::mutex> lock(pool.mu);
-        if (!pool.idle.empty()) { lease.c = pool.idle.back(); pool.idle.pop_back(); }
+        std::lock_guard<std::mutex> lock(g_stream_pool.mu);
+        if (!g_stream_pool.idle.empty()) { lease.c = g_stream_pool.idle.back(); g_stream_pool.idle.pop_back(); }
     }
     if (!lease.c) lease.c = new (std::nothrow) StreamCache;
     if (!lease.c) return ZJ_ERR_OOM;
@@ -650,6 +683,7 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
     pd->user = user;
     for (int k = 0; k < NS; k++) pd->st[k] = st[k];
 
+#define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = cuda_fail(e_, #call); break; } }   // (inside the loop: fall through to the common clean-up)
     const size_t budget = (size_t)(env_mb ? std::max(16, atoi(env_mb)) : 256) << 20;  // device staging per sub-batch
     size_t i = 0;
     int which = 0;
@@ -670,9 +704,10 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         cudaError_t e = cudaSuccess;
         if (pipe) {
             for (int q = 0; q < 3; q++)
-                if (!cache.ev[device][slot][q]) CU(cudaEventCreateWithFlags(&cache.ev[device][slot][q], cudaEventDisableTiming));
+                if (!cache.ev[device][slot][q]) CUB(cudaEventCreateWithFlags(&cache.ev[device][slot][q], cudaEventDisableTiming));
+            if (rc != ZJ_OK) break;
             // the buffer is free once the pixels of its last sub-batch have been downloaded
-            if (cache.ev_rec[device][slot]) CU(cudaStreamWaitEvent(s_up, cache.ev[device][slot][2], 0));
+            if (cache.ev_rec[device][slot]) CUB(cudaStreamWaitEvent(s_up, cache.ev[device][slot][2], 0));
         }
         if (cache.cap[device][slot] < bytes) {
             if (cache.buf[device][slot]) {
@@ -712,15 +747,15 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         }
         if (rc != ZJ_OK) { zj_batch_destroy(b); break; }
         pd->batches.push_back(b);
-        if (pipe) { CU(cudaEventRecord(cache.ev[device][slot][0], s_up)); CU(cudaStreamWaitEvent(s_k, cache.ev[device][slot][0], 0)); }
+        if (pipe) { CUB(cudaEventRecord(cache.ev[device][slot][0], s_up)); CUB(cudaStreamWaitEvent(s_k, cache.ev[device][slot][0], 0)); }
         rc = zj_batch_run(b, s_k);
         if (rc != ZJ_OK) break;
-        if (pipe) { CU(cudaEventRecord(cache.ev[device][slot][1], s_k)); CU(cudaStreamWaitEvent(s_dn, cache.ev[device][slot][1], 0)); }
+        if (pipe) { CUB(cudaEventRecord(cache.ev[device][slot][1], s_k)); CUB(cudaStreamWaitEvent(s_dn, cache.ev[device][slot][1], 0)); }
         for (size_t k = i; k < j; k++) {
             e = cudaMemcpyAsync(out[k], douts[k - i], plans[k].out_size, cudaMemcpyDeviceToHost, s_dn);
             if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
         }
-        if (pipe && rc == ZJ_OK) { CU(cudaEventRecord(cache.ev[device][slot][2], s_dn)); cache.ev_rec[device][slot] = true; }
+        if (pipe && rc == ZJ_OK) { CUB(cudaEventRecord(cache.ev[device][slot][2], s_dn)); cache.ev_rec[device][slot] = true; }
         i = j;
     }
     if (rc == ZJ_OK) {
@@ -731,6 +766,7 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         *pending = pd;
         return ZJ_OK;
     }
+#undef CUB
     const int rc_submit = rc;
     zj_gpu_reconstruct_finish(pd);   // waits for what was queued, releases the descriptors
     return rc_submit;

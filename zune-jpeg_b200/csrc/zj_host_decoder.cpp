@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <new>
 #include <string>
 #include <thread>
@@ -25,6 +26,15 @@
 
 #include "../../include/zune_jpeg_b200.h"
 #include "zj_entropy.h"
+
+// Worker threads pull their work from a shared counter, so a pool that could not be grown (std::system_error: thread limit)
+// just runs with fewer threads -- the calling thread always works too.  Nothing may unwind through the C ABI.
+template <typename Pool, typename Fn>
+static bool spawn(Pool &pool, Fn &fn)
+{
+    try { pool.emplace_back(std::ref(fn)); return true; }
+    catch (...) { return false; }
+}
 
 namespace {
 
@@ -1008,7 +1018,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             }
         };
         std::vector<std::thread> pool;
-        for (size_t t = 1; t < threads; t++) pool.emplace_back(work);
+        for (size_t t = 1; t < threads; t++) if (!spawn(pool, work)) break;
         work();
         for (auto &t : pool) t.join();
         if (bad) return false;
@@ -1089,7 +1099,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             std::atomic<size_t> next{0};
             auto work = [&]() { for (size_t i; (i = next.fetch_add(1)) < pieces.size();) memset(pieces[i].first, 0, pieces[i].second); };
             std::vector<std::thread> pool;
-            for (size_t t = 1; t < threads && t < pieces.size(); t++) pool.emplace_back(work);
+            for (size_t t = 1; t < threads && t < pieces.size(); t++) if (!spawn(pool, work)) break;
             work();
             for (auto &t : pool) t.join();
         };
@@ -1386,6 +1396,8 @@ ZJ_API int zj_decoder_read_headers(zj_decoder *d, const uint8_t *buf, size_t len
         Cursor cur{buf, len, 0};
         d->decode_headers_internal(cur);
     } catch (DecodeError &e) { d->set_error(e); return ZJ_ERR_DECODE; }
+    catch (const std::bad_alloc &) { return ZJ_ERR_OOM; }       // nothing may unwind through the C ABI
+    catch (...) { return ZJ_ERR_DECODE; }
     return ZJ_OK;
 }
 ZJ_API int zj_decoder_info(const zj_decoder *d, zj_image_info *info)
@@ -1401,6 +1413,8 @@ ZJ_API int zj_decoder_decode_coefficients(zj_decoder *d, const uint8_t *buf, siz
     if (!d || (!buf && len) || !img) return ZJ_ERR_INVALID_ARG;
     d->clear_error();
     try { d->host_stage(buf, len, img); } catch (DecodeError &e) { d->set_error(e); return ZJ_ERR_DECODE; }
+    catch (const std::bad_alloc &) { return ZJ_ERR_OOM; }
+    catch (...) { return ZJ_ERR_DECODE; }
     return ZJ_OK;
 }
 
@@ -1537,11 +1551,55 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
         give_back(dec[1]);
     };
     std::vector<std::thread> pool;
-    for (size_t t = 1; t < nthreads; t++) pool.emplace_back(worker);
+    for (size_t t = 1; t < nthreads; t++) if (!spawn(pool, worker)) break;
     if (n) worker();
     for (auto &t : pool) t.join();
     return failed.load();
 }
+// ---- state zj_decode_batch_gpu[_device] keeps between calls: two slots of device staging memory (at least 1 GB each once
+// used, grown to the sub-batch budget), their streams and pinned descriptor / status blocks.  zj_release_device_caches frees
+// them; a buffer larger than ZJ_RETAIN_MB (default 1024) is freed when the call that grew it ends.
+struct GpuSlot {
+    cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
+    zj_batch *batch = nullptr;
+    std::vector<size_t> take, idx;            // images of the sub-batch in stage 1 / images whose pixels are on their way
+    std::vector<zj::EntImage> eimg;
+    std::vector<uint8_t *> pix;
+    std::vector<size_t> st_off;
+    uint8_t *meta_host = nullptr, *st_host = nullptr;   // pinned: descriptors + tables + interval starts up, statuses down
+    size_t meta_cap = 0, st_cap = 0;
+    bool staged = false;
+    void release()      // streams, device staging memory and the pinned descriptor / status blocks
+    {
+        if (mem) cudaFree(mem);
+        if (s) cudaStreamDestroy(s);
+        if (meta_host) cudaFreeHost(meta_host);
+        if (st_host) cudaFreeHost(st_host);
+        *this = GpuSlot{};
+    }
+};
+struct GpuSlotCache { GpuSlot slot[2]; int device = -1; };
+static std::mutex g_slot_mu;
+static GpuSlotCache g_slot_cache;
+static size_t slot_retain_bytes()
+{
+    static const size_t v = [] { const char *e = getenv("ZJ_RETAIN_MB"); long mb = e ? atol(e) : 1024; return (size_t)(mb < 0 ? 0 : mb) << 20; }();
+    return v;
+}
+extern "C" void zj_capi_release_stream_caches(void);   // zj_capi.cu (hidden)
+
+ZJ_API void zj_release_device_caches(void)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_slot_mu);     // (waits for a zj_decode_batch_gpu call in flight)
+        if (g_slot_cache.device >= 0 && cudaSetDevice(g_slot_cache.device) == cudaSuccess)
+            for (auto &sl : g_slot_cache.slot) sl.release();
+        g_slot_cache.device = -1;
+        cudaGetLastError();
+    }
+    zj_capi_release_stream_caches();
+}
+
 // Batch front door with the entropy stage on the GPU as well (zj_entropy.cu) for the JPEGs that allow it: baseline scans
 // with restart markers whose every interval ends the way the reference's sequential loop ends it.  Those upload their FILE
 // (not their coefficient planes: 12 MB instead of 201 MB for an 8192x8192 image), are entropy-decoded one restart interval per
@@ -1600,7 +1658,7 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
             }
         };
         std::vector<std::thread> pool;
-        for (size_t t = 1; t < std::min(nthreads, n); t++) pool.emplace_back(work);
+        for (size_t t = 1; t < std::min(nthreads, n); t++) if (!spawn(pool, work)) break;
         if (n) work();
         for (auto &t : pool) t.join();
     }
@@ -1642,7 +1700,10 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     for (size_t i = 0; i < n; i++) if (!items[i].gpu) { is_early[i] = 1; early_list.push_back(i); }
     int early_rc = 0;
     std::thread early;
-    if (!early_list.empty()) early = std::thread([&]() { cudaSetDevice(opt.device); early_rc = run_host(early_list); });
+    if (!early_list.empty()) {
+        try { early = std::thread([&]() { cudaSetDevice(opt.device); early_rc = run_host(early_list); }); }
+        catch (...) { early_rc = run_host(early_list); }      // no thread to be had: do it here, before the GPU phase
+    }
     // ---- GPU: sub-batches of as many images as fit the staging budget, two slots in flight.  Stage 1 of sub-batch b (upload,
     // clear the planes, entropy kernel, status download) is queued before the host waits for the statuses of sub-batch b-1 and
     // queues its stage 2 (reconstruction, pixel download), so the two streams keep the GPU and both PCIe directions busy.
@@ -1655,17 +1716,6 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     };
     const char *env_mb = getenv("ZJ_GPU_ENTROPY_BUDGET_MB");
     const size_t budget = (size_t)(env_mb ? std::max(64, atoi(env_mb)) : (dev_out ? 8192 : 4096)) << 20;   // host outputs: smaller sub-batches, so that the download of one overlaps the kernels of the next (2 GB and 8 GB measured slower)
-    struct Slot {
-        cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
-        zj_batch *batch = nullptr;
-        std::vector<size_t> take, idx;            // images of the sub-batch in stage 1 / images whose pixels are on their way
-        std::vector<zj::EntImage> eimg;
-        std::vector<uint8_t *> pix;
-        std::vector<size_t> st_off;
-        uint8_t *meta_host = nullptr, *st_host = nullptr;   // pinned: descriptors + tables + interval starts up, statuses down
-        size_t meta_cap = 0, st_cap = 0;
-        bool staged = false;
-    };
     auto pinned_grow = [](uint8_t *&p, size_t &cap, size_t need) -> bool {
         if (cap >= need) return true;
         if (p) cudaFreeHost(p);
@@ -1677,28 +1727,19 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     };
     // the two slots' streams and device memory are kept between calls (allocating and freeing gigabytes costs 3-13 ms per
     // call and synchronises the device); one call at a time uses them, a concurrent call works with slots of its own
-    struct SlotCache { Slot slot[2]; int device = -1; };
-    static std::mutex cache_mu;
-    static SlotCache cache;
-    SlotCache own;
-    std::unique_lock<std::mutex> cache_lock(cache_mu, std::try_to_lock);
-    SlotCache &sc = cache_lock.owns_lock() ? cache : own;
+    GpuSlotCache own;
+    std::unique_lock<std::mutex> cache_lock(g_slot_mu, std::try_to_lock);
+    GpuSlotCache &sc = cache_lock.owns_lock() ? g_slot_cache : own;
     bool cuda_ok = cudaSetDevice(opt.device) == cudaSuccess;
     if (cuda_ok && sc.device != opt.device) {
-        for (auto &sl : sc.slot) {
-            if (sl.mem) cudaFree(sl.mem);
-            if (sl.s) cudaStreamDestroy(sl.s);
-            if (sl.meta_host) cudaFreeHost(sl.meta_host);
-            if (sl.st_host) cudaFreeHost(sl.st_host);
-            sl = Slot{};
-        }
+        for (auto &sl : sc.slot) sl.release();
         sc.device = opt.device;
     }
-    Slot *slot = sc.slot;
+    GpuSlot *slot = sc.slot;
     for (int k = 0; k < 2 && cuda_ok; k++)
         if (!slot[k].s) cuda_ok = cudaStreamCreateWithFlags(&slot[k].s, cudaStreamNonBlocking) == cudaSuccess;
     std::vector<uint8_t *> malloced(n, nullptr);
-    auto drain = [&](Slot &sl) {   // wait for the slot's downloads, publish its images
+    auto drain = [&](GpuSlot &sl) {   // wait for the slot's downloads, publish its images
         if (sl.idx.empty() && !sl.batch) return;
         const bool ok = cudaStreamSynchronize(sl.s) == cudaSuccess;
         if (!ok) cudaGetLastError();
@@ -1708,7 +1749,7 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     };
     size_t i0 = 0;
     // stage 1: false when there is nothing (left) to queue
-    auto stage1 = [&](Slot &sl) -> bool {
+    auto stage1 = [&](GpuSlot &sl) -> bool {
         sl.staged = false;
         sl.take.clear();
         size_t bytes = 0, i1 = i0;
@@ -1798,7 +1839,7 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         return true;
     };
     // stage 2: the statuses are in; accepted images are reconstructed from their device planes and downloaded
-    auto stage2 = [&](Slot &sl) {
+    auto stage2 = [&](GpuSlot &sl) {
         if (!sl.staged) return;
         sl.staged = false;
         if (cudaStreamSynchronize(sl.s) != cudaSuccess) { cudaGetLastError(); return; }
@@ -1835,7 +1876,7 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         int cur = 0;
         bool more = true;
         while (more) {
-            Slot &sl = slot[cur];
+            GpuSlot &sl = slot[cur];
             drain(sl);
             more = stage1(sl);
             stage2(slot[cur ^ 1]);   // (measured: queueing it before stage 1 instead is no faster, and slower with small sub-batches)
@@ -1847,11 +1888,10 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     for (int k = 0; k < 2; k++) {
         drain(slot[k]);
         slot[k].take.clear();
-        if (&sc == &own) {
-            if (slot[k].mem) cudaFree(slot[k].mem);
-            if (slot[k].s) cudaStreamDestroy(slot[k].s);
-            if (slot[k].meta_host) cudaFreeHost(slot[k].meta_host);
-            if (slot[k].st_host) cudaFreeHost(slot[k].st_host);
+        if (&sc == &own) slot[k].release();
+        else if (slot[k].cap > slot_retain_bytes()) {      // a buffer that grew past the retention cap goes back to the driver
+            cudaFree(slot[k].mem);
+            slot[k].mem = nullptr; slot[k].cap = 0;
         }
     }
     if (cache_lock.owns_lock()) cache_lock.unlock();
