@@ -127,6 +127,25 @@ ZJ_API int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *i
                                      uint8_t *const *out, const size_t *out_len, zj_pending **pending);
 ZJ_API int zj_gpu_reconstruct_finish(zj_pending *pending);
 
+/* Several devices of one box (north_star: "batches of images (and, for single huge images, restart-interval strips) are
+ * partitioned across the GPUs with independent streams, no NCCL: the work shards with no reduction").  n >= n_dev: contiguous
+ * image ranges, one per device (zj_partition).  n < n_dev: every image is cut into contiguous STRIP ranges, one per device
+ * (zj_image_strip_range): worker::post_process (src/worker.rs:32-85) is called per strip and every rule in it is local to
+ * that strip, so a device needs only its strips' coefficient rows and writes only its rows.  One host thread per device
+ * drives zj_gpu_reconstruct on that device's streams.  Host pointers, as zj_gpu_reconstruct. */
+ZJ_API int zj_gpu_reconstruct_multi(const int *devices, size_t n_dev, const zj_image *imgs, size_t n,
+                                    uint8_t *const *out, const size_t *out_len);
+/* [begin, end) of part `part` when n_items are cut into n_parts contiguous, balanced ranges (sizes differ by at most one). */
+ZJ_API void zj_partition(size_t n_items, size_t n_parts, size_t part, size_t *begin, size_t *end);
+/* Strips [strip_begin, strip_end) of `img` as an image of their own: *sub = the descriptor (planes advanced to the first
+ * strip, height = the range's rows; the range that ends at the last strip also owns the rows below it), *out_offset /
+ * *out_bytes = where its pixels live inside the whole image's output.  *n_strips = strips of the whole image (pass sub,
+ * out_offset, out_bytes = NULL to query only that).  Reconstructing every range of a partition gives exactly the bytes of
+ * reconstructing the whole image.  ZJ_ERR_UNSUPPORTED: this image cannot be cut (its strip count was limited by the
+ * reference's output-capacity rule, mcu_prog.rs:206-209). */
+ZJ_API int zj_image_strip_range(const zj_image *img, uint32_t strip_begin, uint32_t strip_end, zj_image *sub,
+                                size_t *out_offset, size_t *out_bytes, uint32_t *n_strips);
+
 /* DEVICE entry point: coefficient planes and outputs already live in the memory of `device`.
  * Asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream); no host<->device pixel traffic.
  * Device coefficient planes must start on a 16-byte boundary (ZJ_ERR_INVALID_ARG otherwise; cudaMalloc'ed memory
@@ -276,6 +295,12 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
                            uint8_t **out, size_t *out_len, int *status);
 /* zj_decode_batch keeps its workers' decoders (pinned coefficient planes sized for the largest image seen, two per host
  * thread) for the next call; this frees them. */
+/* zj_decode_batch over several devices of one box: contiguous image ranges, one per device, each range decoded by its own
+ * share of the host threads (o->num_threads / n_dev each; o->device is ignored) and reconstructed on its device.  With
+ * fewer images than devices every image is entropy-decoded by all host threads (restart intervals side by side) and its
+ * strips are spread over the devices (zj_gpu_reconstruct_multi). */
+ZJ_API int zj_decode_batch_multi(const zj_options *o, const int *devices, size_t n_dev, const uint8_t *const *bufs,
+                                 const size_t *lens, size_t n, uint8_t **out, size_t *out_len, int *status);
 ZJ_API void zj_release_host_caches(void);
 /* Device-side state kept between calls, and its release.  zj_gpu_reconstruct[_submit] keeps, per host thread that called it,
  * its staging streams and up to three device staging buffers (256 MB sub-batches by default); zj_decode_batch_gpu[_device]

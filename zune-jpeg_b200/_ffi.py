@@ -96,6 +96,11 @@ SYMBOLS = {
     "zj_gpu_reconstruct": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
     "zj_gpu_reconstruct_submit": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t), _PP]),
     "zj_gpu_reconstruct_finish": (C.c_int, [_P]),
+    "zj_gpu_reconstruct_multi": (C.c_int, [C.POINTER(C.c_int), C.c_size_t, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
+    "zj_partition": (None, [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "zj_image_strip_range": (C.c_int, [C.POINTER(ZjImage), C.c_uint32, C.c_uint32, C.POINTER(ZjImage), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]),
+    "zj_decode_batch_multi": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(C.c_int), C.c_size_t, C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
+                                        C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "zj_gpu_reconstruct_device": (C.c_int, [C.c_int, _P, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
     "zj_batch_create": (C.c_int, [C.c_int, C.POINTER(ZjImage), C.c_size_t, _PP, C.POINTER(C.c_size_t), _PP]),
     "zj_batch_run": (C.c_int, [_P, _P]),

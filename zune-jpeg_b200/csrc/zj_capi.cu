@@ -11,6 +11,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/zune_jpeg_b200.h"
@@ -770,6 +771,126 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
     const int rc_submit = rc;
     zj_gpu_reconstruct_finish(pd);   // waits for what was queued, releases the descriptors
     return rc_submit;
+}
+
+// ------------------------------------------------------------------------------------------ several devices
+// The path shards with no exchange step: images are independent, and so are the strips of one image --
+// every rule of worker::post_process is local to the strip it is called for (worker.rs:32-85 sees one strip's coefficients
+// and one strip's output rows).  So a batch is cut into contiguous image ranges, one per device, and a batch with fewer
+// images than devices is cut inside the images: contiguous STRIP ranges, each a "virtual image" whose planes start at the
+// range's first strip and whose output starts at the range's first row.  One host thread per device runs its share through
+// zj_gpu_reconstruct on that device's own streams; nothing is exchanged between devices.
+void zj_partition(size_t n_items, size_t n_parts, size_t part, size_t *begin, size_t *end)
+{
+    size_t lo = 0, hi = 0;
+    if (n_parts && part < n_parts) {
+        const size_t base = n_items / n_parts, rem = n_items % n_parts;
+        lo = part * base + std::min(part, rem);
+        hi = lo + base + (part < rem ? 1 : 0);
+    }
+    if (begin) *begin = lo;
+    if (end) *end = hi;
+}
+
+int zj_image_strip_range(const zj_image *img, uint32_t strip_begin, uint32_t strip_end, zj_image *sub, size_t *out_offset, size_t *out_bytes,
+                         uint32_t *n_strips)
+{
+    Plan pl;
+    int rc = plan_image(img, &pl);
+    if (rc) return rc;
+    if (n_strips) *n_strips = pl.n_strips;
+    if (!sub && !out_offset && !out_bytes) return ZJ_OK;           // a query for the strip count
+    if (strip_begin > strip_end || strip_end > pl.n_strips) return ZJ_ERR_INVALID_ARG;
+    const size_t row_bytes = (size_t)img->width * num_components(img->out_cs);
+    // the range that holds the last strip also owns the rows below it; an image without strips is one (empty) range at 0
+    const bool last = strip_end == pl.n_strips && (strip_begin < strip_end || pl.n_strips == 0);
+    if (strip_begin == strip_end && !last) {
+        if (out_offset) *out_offset = 0;
+        if (out_bytes) *out_bytes = 0;
+        if (sub) { *sub = *img; sub->height = 0; }
+        return ZJ_OK;
+    }
+    const uint64_t row0 = (uint64_t)strip_begin * pl.rows;
+    if (row0 > img->height) return ZJ_ERR_INVALID_ARG;
+    // the last range also owns the rows below the last strip (a partial strip, and the rows the reference never writes: Q1)
+    const uint32_t h = last ? img->height - (uint32_t)row0 : (strip_end - strip_begin) * pl.rows;
+    if (!last && row0 + h > img->height) return ZJ_ERR_INVALID_ARG;
+
+    if (out_offset) *out_offset = (size_t)row0 * row_bytes;
+    if (out_bytes) *out_bytes = (size_t)h * row_bytes;
+    if (sub) {
+        *sub = *img;
+        sub->height = h;
+        for (uint32_t z = 0; z < img->n_comp; z++) {
+            const uint64_t skip = (uint64_t)strip_begin * pl.chunk[z];
+            if (img->comp[z].coeff) sub->comp[z].coeff = img->comp[z].coeff + skip;
+            sub->comp[z].n_i16 = img->comp[z].n_i16 > skip ? img->comp[z].n_i16 - skip : 0;
+        }
+        if (h == 0) return ZJ_OK;
+        // the virtual image must plan to exactly the strips of the range (it does unless the whole image's strip count was
+        // cut by the reference's output-capacity rule, mcu_prog.rs:206-209 -- widths next to 65535 only)
+        Plan ps;
+        rc = plan_image(sub, &ps);
+        if (rc) return rc;
+        if (ps.n_strips != strip_end - strip_begin) return ZJ_ERR_UNSUPPORTED;
+    }
+    return ZJ_OK;
+}
+
+int zj_gpu_reconstruct_multi(const int *devices, size_t n_dev, const zj_image *imgs, size_t n, uint8_t *const *out, const size_t *out_len)
+{
+    if (!devices || n_dev == 0 || ((!imgs || !out || !out_len) && n)) return ZJ_ERR_INVALID_ARG;
+    if (n == 0) return ZJ_OK;
+    // per device: a list of (virtual) images with their output slices
+    struct Share { std::vector<zj_image> imgs; std::vector<uint8_t *> out; std::vector<size_t> len; int rc = ZJ_OK; };
+    std::vector<Share> share(n_dev);
+    bool by_strips = n < n_dev;
+    if (by_strips) {
+        for (size_t i = 0; i < n && by_strips; i++) {
+            uint32_t ns = 0;
+            int rc = zj_image_strip_range(&imgs[i], 0, 0, nullptr, nullptr, nullptr, &ns);
+            if (rc) return rc;
+            if (!out[i]) return ZJ_ERR_INVALID_ARG;
+            if (out_len[i] < zj_output_size(&imgs[i])) return ZJ_ERR_SHORT_OUTPUT;
+            std::vector<Share> trial(n_dev);
+            for (size_t k = 0; k < n_dev; k++) {
+                size_t s0, s1;
+                zj_partition(ns, n_dev, k, &s0, &s1);
+                if (s0 == s1 && !(ns == 0 && k == 0)) continue;   // (an image without strips: its never-written rows go to the first device)
+                zj_image sub;
+                size_t off = 0, bytes = 0;
+                rc = zj_image_strip_range(&imgs[i], (uint32_t)s0, (uint32_t)s1, &sub, &off, &bytes, nullptr);
+                if (rc == ZJ_ERR_UNSUPPORTED) { by_strips = false; break; }   // cannot be cut: whole images per device instead
+                if (rc) return rc;
+                if (bytes == 0) continue;
+                share[k].imgs.push_back(sub); share[k].out.push_back(out[i] + off); share[k].len.push_back(bytes);
+            }
+        }
+        if (!by_strips) for (auto &sh : share) { sh.imgs.clear(); sh.out.clear(); sh.len.clear(); }
+    }
+    if (!by_strips) {
+        for (size_t k = 0; k < n_dev; k++) {
+            size_t lo, hi;
+            zj_partition(n, n_dev, k, &lo, &hi);
+            share[k].imgs.assign(imgs + lo, imgs + hi);
+            share[k].out.assign(out + lo, out + hi);
+            share[k].len.assign(out_len + lo, out_len + hi);
+        }
+    }
+    auto run = [&](size_t k) {
+        Share &sh = share[k];
+        if (sh.imgs.empty()) return;
+        try { sh.rc = zj_gpu_reconstruct(devices[k], nullptr, sh.imgs.data(), sh.imgs.size(), sh.out.data(), sh.len.data()); }
+        catch (...) { sh.rc = ZJ_ERR_OOM; }
+    };
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < n_dev; k++) {
+        try { pool.emplace_back(run, k); } catch (...) { run(k); }
+    }
+    run(0);
+    for (auto &t : pool) t.join();
+    for (size_t k = 0; k < n_dev; k++) if (share[k].rc != ZJ_OK) return share[k].rc;
+    return ZJ_OK;
 }
 
 int zj_gpu_reconstruct(int device, void *stream, const zj_image *imgs, size_t n, uint8_t *const *out, const size_t *out_len)

@@ -1517,7 +1517,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
             if (i >= n) break;
             if (!dec[cur]) dec[cur] = take_decoder();
             zj_decoder *d = dec[cur];
-            if (!d) { status[i] = ZJ_ERR_OOM; failed++; continue; }
+            if (!d) { status[i] = ZJ_ERR_OOM; out_len[i] = 0; failed++; continue; }
             zj_image img;
             int rc = (!bufs[i] && lens[i]) ? ZJ_ERR_INVALID_ARG : zj_decoder_decode_coefficients(d, bufs[i], lens[i], &img);
             size_t need = 0;
@@ -1556,6 +1556,62 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
     for (auto &t : pool) t.join();
     return failed.load();
 }
+// zj_decode_batch over several devices (contiguous image ranges, no exchange between devices)
+ZJ_API int zj_decode_batch_multi(const zj_options *o, const int *devices, size_t n_dev, const uint8_t *const *bufs,
+                                 const size_t *lens, size_t n, uint8_t **out, size_t *out_len, int *status)
+{
+    if (!devices || n_dev == 0 || ((!bufs || !lens || !out || !out_len || !status) && n)) return ZJ_ERR_INVALID_ARG;
+    zj_options opt;
+    if (o) opt = *o; else zj_options_default(&opt);
+    size_t nthreads = opt.num_threads ? opt.num_threads : std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    if (n >= n_dev) {
+        std::vector<int> rcs(n_dev, 0);
+        auto run = [&](size_t k) {
+            size_t lo, hi;
+            zj_partition(n, n_dev, k, &lo, &hi);
+            if (lo == hi) return;
+            zj_options ok = opt;
+            ok.device = devices[k];
+            ok.num_threads = (uint32_t)std::max<size_t>(1, nthreads / n_dev);
+            cudaSetDevice(devices[k]);
+            rcs[k] = zj_decode_batch(&ok, bufs + lo, lens + lo, hi - lo, out + lo, out_len + lo, status + lo);
+        };
+        std::vector<std::thread> pool;
+        for (size_t k = 1; k < n_dev; k++) {
+            try { pool.emplace_back(run, k); } catch (...) { run(k); }
+        }
+        run(0);
+        for (auto &t : pool) t.join();
+        int failed = 0;
+        for (int rc : rcs) { if (rc < 0) return rc; failed += rc; }
+        return failed;
+    }
+    // fewer images than devices: one image at a time, all host threads on its restart intervals, its strips over the devices
+    int failed = 0;
+    opt.num_threads = (uint32_t)nthreads;
+    opt.device = devices[0];
+    for (size_t i = 0; i < n; i++) {
+        zj_decoder *d = zj_decoder_new(&opt);
+        zj_image img;
+        int rc = !d ? (int)ZJ_ERR_OOM : ((!bufs[i] && lens[i]) ? (int)ZJ_ERR_INVALID_ARG : zj_decoder_decode_coefficients(d, bufs[i], lens[i], &img));
+        size_t need = 0;
+        if (rc == ZJ_OK) { need = zj_output_size(&img); rc = zj_validate_image(&img); if (rc == ZJ_OK && need == 0) rc = ZJ_ERR_INVALID_ARG; }
+        uint8_t *dst = out[i];
+        bool mine = false;
+        if (rc == ZJ_OK) {
+            if (dst) { if (out_len[i] < need) rc = ZJ_ERR_SHORT_OUTPUT; }
+            else { dst = (uint8_t *)malloc(need); mine = true; if (!dst) rc = ZJ_ERR_OOM; }
+        }
+        if (rc == ZJ_OK) rc = zj_gpu_reconstruct_multi(devices, n_dev, &img, 1, &dst, &need);
+        if (rc == ZJ_OK) { out[i] = dst; out_len[i] = need; }
+        else { if (mine) free(dst); if (mine || !out[i]) out[i] = nullptr; out_len[i] = 0; failed++; }
+        status[i] = rc;
+        if (d) zj_decoder_free(d);
+    }
+    return failed;
+}
+
 // ---- state zj_decode_batch_gpu[_device] keeps between calls: two slots of device staging memory (at least 1 GB each once
 // used, grown to the sub-batch budget), their streams and pinned descriptor / status blocks.  zj_release_device_caches frees
 // them; a buffer larger than ZJ_RETAIN_MB (default 1024) is freed when the call that grew it ends.

@@ -286,12 +286,15 @@ DecoderOptions = ZuneJpegOptions
 
 
 def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int = 0, out=None, gpu_entropy: bool = False, stats: dict | None = None,
-                 device_out=None):
+                 device_out=None, desc=None, devices=None):
     """zj_decode_batch: JPEG byte strings in, pixel bytes out, `threads` host threads (0 = one per hardware thread)
     running the host stage of different images side by side while the GPU reconstructs the finished ones.
     `gpu_entropy=True` (zj_decode_batch_gpu): baseline JPEGs with restart markers are entropy-decoded on the GPU as well, one
     restart interval per thread; same results, `stats["gpu_entropy"]` = how many images took that route.
-    `device_out=[(device_ptr, nbytes), ...]` (zj_decode_batch_gpu_device): the pixels stay in device memory.
+    `device_out=[(device_ptr, nbytes), ...]` (zj_decode_batch_gpu_device): the pixels stay in device memory; with
+    `desc=gpu.OutputDesc(...)` (zj_decode_batch_gpu_device_ex) in the layout / type / scale a GPU consumer wants.
+    `devices=[0, 1, ...]` (zj_decode_batch_multi): the batch is cut into contiguous image ranges, one per device of the box
+    (strip ranges when there are fewer images than devices).
 
     Returns a list with one entry per input: `bytes` (or, with `out` / `device_out`, the number of bytes written) for a decoded
     image, a `DecodeErrors` instance for a failed one.  `out`: optional list of writable buffers (e.g. PinnedBuffer.array
@@ -318,10 +321,16 @@ def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int =
         for i, v in enumerate(views):
             outs[i] = v.ctypes.data
             out_len[i] = v.nbytes
-    if gpu_entropy or device_out is not None:
+    if devices is not None:
+        devs = (C.c_int * len(devices))(*devices)
+        rc = lib.zj_decode_batch_multi(C.byref(raw), devs, len(devices), bufs, lens, n, outs, out_len, status)
+    elif gpu_entropy or device_out is not None:
         n_gpu = C.c_size_t(0)
-        fn = lib.zj_decode_batch_gpu_device if device_out is not None else lib.zj_decode_batch_gpu
-        rc = fn(C.byref(raw), bufs, lens, n, outs, out_len, status, C.byref(n_gpu))
+        if device_out is not None and desc is not None:
+            rc = lib.zj_decode_batch_gpu_device_ex(C.byref(raw), bufs, lens, n, C.byref(desc.c), outs, out_len, status, C.byref(n_gpu))
+        else:
+            fn = lib.zj_decode_batch_gpu_device if device_out is not None else lib.zj_decode_batch_gpu
+            rc = fn(C.byref(raw), bufs, lens, n, outs, out_len, status, C.byref(n_gpu))
         if stats is not None:
             stats["gpu_entropy"] = int(n_gpu.value)
     else:

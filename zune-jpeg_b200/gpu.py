@@ -68,6 +68,25 @@ def reconstruct(images, device: int = 0, stream=None):
     return outs
 
 
+def reconstruct_multi(images, devices):
+    """zj_gpu_reconstruct_multi: one batch over several devices of one box (image ranges, or strip ranges when there are fewer
+    images than devices); host planes in, host pixels out."""
+    lib = _ffi.load()
+    n = len(images)
+    arr = _img_array(images)
+    outs, ptrs, lens = [], (C.c_void_p * n)(), (C.c_size_t * n)()
+    for i, im in enumerate(images):
+        sz = output_size(im)
+        if sz == 0:
+            _check(validate(im) or _ffi.ERR_INVALID_ARG, "zj_validate_image")
+        o = np.empty(sz, np.uint8)
+        outs.append(o)
+        ptrs[i], lens[i] = o.ctypes.data, sz
+    devs = (C.c_int * len(devices))(*devices)
+    _check(lib.zj_gpu_reconstruct_multi(devs, len(devices), arr, n, ptrs, lens), "zj_gpu_reconstruct_multi")
+    return outs
+
+
 class DeviceBuffer:
     """cudaMalloc'd bytes owned through the C ABI."""
 

@@ -8,18 +8,40 @@ import os
 
 
 def partition(n_items: int, world: int, rank: int) -> range:
-    """Contiguous, balanced slice of [0, n_items) owned by `rank` (sizes differ by at most one)."""
+    """Contiguous, balanced slice of [0, n_items) owned by `rank` (sizes differ by at most one): zj_partition, the rule the
+    library's own multi-device entry points (zj_gpu_reconstruct_multi, zj_decode_batch_multi) cut batches with."""
     if world <= 0 or not (0 <= rank < world):
         raise ValueError("bad world/rank")
-    base, rem = divmod(n_items, world)
-    lo = rank * base + min(rank, rem)
-    return range(lo, lo + base + (1 if rank < rem else 0))
+    import ctypes as C
+    from . import _ffi
+    lo, hi = C.c_size_t(), C.c_size_t()
+    _ffi.load().zj_partition(n_items, world, rank, C.byref(lo), C.byref(hi))
+    return range(lo.value, hi.value)
 
 
-def strip_partition(n_strips: int, world: int, rank: int) -> range:
-    """A single huge image: contiguous strip ranges per GPU (restart intervals make the host entropy stage
-    splittable on the same boundaries)."""
-    return partition(n_strips, world, rank)
+def strip_ranges(img, world: int):
+    """A single huge image: [(sub-image descriptor, byte offset, byte count)] of the contiguous strip ranges the devices of
+    one box take (zj_image_strip_range); ranges without rows are left out.  Every rule of the path is strip-local, so the
+    ranges' pixels concatenate to the whole image's."""
+    import ctypes as C
+    from . import _ffi
+    lib = _ffi.load()
+    ns = C.c_uint32()
+    rc = lib.zj_image_strip_range(C.byref(img), 0, 0, None, None, None, C.byref(ns))
+    if rc:
+        raise ValueError(f"zj_image_strip_range: {rc}")
+    out = []
+    for r in range(world):
+        p = partition(ns.value, world, r)
+        if len(p) == 0 and not (ns.value == 0 and r == 0):
+            continue
+        sub, off, nb = _ffi.ZjImage(), C.c_size_t(), C.c_size_t()
+        rc = lib.zj_image_strip_range(C.byref(img), p.start, p.stop, C.byref(sub), C.byref(off), C.byref(nb), None)
+        if rc:
+            raise ValueError(f"zj_image_strip_range: {rc}")
+        if nb.value:
+            out.append((sub, off.value, nb.value))
+    return out
 
 
 def env_world():
