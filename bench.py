@@ -411,14 +411,24 @@ def run_ours(args):
     # ---- e2e: zj_gpu_reconstruct with pinned HOST planes and pinned HOST outputs (H2D + kernels + D2H timed)
     e2e = None
     if not args.no_e2e:
-        pinned_planes = []
+        # (an image's planes in ONE pinned block, each on a 256-byte boundary -- the layout the host stage decodes into:
+        # zj_gpu_reconstruct uploads planes that follow each other with a single copy)
+        class _Ptr:
+            def __init__(self, ptr):
+                self.ptr = ptr
+        pinned_planes, pinned_blocks = [], []
         for (img, planes, _jpeg) in pool:
-            row = []
+            offs, tot = [], 0
             for p in planes:
+                offs.append(tot)
+                tot += (p.nbytes + 255) & ~255
+            blk = gpu.PinnedBuffer(max(tot, 1))
+            pinned_blocks.append(blk)
+            row = []
+            for p, o in zip(planes, offs):
                 if p.nbytes:
-                    pb = gpu.PinnedBuffer(p.nbytes)
-                    pb.array[:] = p.view(np.uint8)
-                    row.append(pb)
+                    blk.array[o:o + p.nbytes] = p.view(np.uint8)
+                    row.append(_Ptr(blk.ptr + o))
                 else:
                     row.append(None)
             pinned_planes.append(row)
@@ -553,6 +563,20 @@ def run_ours(args):
                 raise SystemExit("bench.py: single-image decode differs from the oracle")
             single[label] = {"threads": nt, "intervals_side_by_side": int(seg), "host_stage_ms": round(best_h * 1e3, 2),
                              "total_ms": round(best_t * 1e3, 2), "MP/s": round(w * h / 1e6 / best_t, 1)}
+        # ... and as a strip pipeline (zj_decoder_decode_into): finished strip ranges go through the GPU while the
+        # host is still entropy-decoding the rest of the image
+        for label, nt in (("sequential_pipelined", 1), ("parallel_pipelined", threads)):
+            d1 = Decoder.new_with_options(opts.set_num_threads(nt))
+            best_t, seg = 1e9, 0
+            for _ in range(4):
+                l0 = gpu.launch_count()
+                t0 = time.perf_counter()
+                d1.decode_into(jpegs[0], pinned_dec.array[:out_bytes])
+                best_t, seg = min(best_t, time.perf_counter() - t0), d1.entropy_segments()
+                ranges = gpu.launch_count() - l0
+            if not args.no_check and not np.array_equal(pinned_dec.array[:out_bytes], want):
+                raise SystemExit("bench.py: pipelined single-image decode differs from the oracle")
+            single[label] = {"threads": nt, "intervals_side_by_side": int(seg), "strip_ranges": int(ranges), "total_ms": round(best_t * 1e3, 2), "MP/s": round(w * h / 1e6 / best_t, 1)}
         decode["single_image"] = single
     # ---- the entropy stage on the GPU as well (zj_decode_batch_gpu: one restart interval per GPU thread).  Needs restart markers:
     # configs without them (c2) are measured on the same images encoded with one restart interval per MCU row, and say so.
@@ -622,9 +646,9 @@ def run_ours(args):
                 b_.free()
 
     # ---- device-side consumer on the resident batch: coefficient planes in HBM -> normalised planar f16 in HBM
-    # through zj_gpu_reconstruct_device_ex (reconstruction kernel + consumer kernel per L2-sized sub-batch)
+    # through zj_gpu_reconstruct_device_ex (reconstruction kernel + consumer kernel per sub-batch of at most 1 GB of u8)
     consumer = None
-    if rank == 0 and world == 1 and not args.no_decode and not gray:
+    if rank == 0 and world == 1 and not args.no_consumer and not gray:
         from zune_jpeg_b200 import _ffi
         lib = _ffi.load()
         desc_f16 = gpu.OutputDesc("CHW", "f16", False, 3, IMAGENET_MEAN, IMAGENET_INV_STD)
@@ -654,11 +678,11 @@ def run_ours(args):
             got16 = f16_out[0].download(stream=stream.ptr).view(np.float16).reshape(3, h, w)
             if got16.tobytes() != desc_f16.expected(want, w, h, len(want) // (w * h)).tobytes():
                 raise SystemExit("bench.py: consumer output differs from the specification applied to the oracle's pixels")
-        c_algo = algo_bytes / batch * nb_c - out_bytes * nb_c + f16_bytes * nb_c      # coefficients in + f16 out (the u8 intermediate is meant to stay in L2)
+        c_algo = algo_bytes / batch * nb_c + out_bytes * nb_c + f16_bytes * nb_c      # coefficients in + u8 out and in again + f16 out (two kernels)
         consumer = {"value": round(nb_c * w * h / 1e6 / (ms_c / 1e3), 2), "unit": "MP/s", "images": nb_c, "ms_per_step": round(ms_c, 4),
                     "launches_per_step": int((gpu.launch_count() - l0) // k_c), "algorithmic_bytes_per_step": int(c_algo),
                     "hbm_frac": round(c_algo / (ms_c / 1e3) / 1e9 / float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else c_algo / (ms_c / 1e3) / 1e9 / 6650.0, 4),
-                    "how": "zj_gpu_reconstruct_device_ex: resident coefficient planes -> (u8 - mean) * inv_std, planar f16, resident; the interleaved u8 intermediate is produced and consumed per 48 MB sub-batch"}
+                    "how": "zj_gpu_reconstruct_device_ex: resident coefficient planes -> (u8 - mean) * inv_std, planar f16, resident; two kernels per sub-batch of at most 1 GB of interleaved u8 (written once, read once)"}
         for b_ in f16_out:
             b_.free()
 
@@ -728,6 +752,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true", help="skip the whole-decode (JPEG bytes -> pixels) measurement")
     ap.add_argument("--decode-images", type=int, default=256,
                     help="images of the whole-decode leg: one per host thread is in its (ragged) last round, so few images under-report")
+    ap.add_argument("--no-consumer", action="store_true", help="skip the device-side consumer leg (planes -> normalised planar f16)")
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

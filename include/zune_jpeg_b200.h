@@ -194,8 +194,8 @@ ZJ_API int zj_consumer_output_shape(const zj_image *img, const zj_output_desc *d
 ZJ_API int zj_gpu_convert_device(int device, void *stream, const uint8_t *src_dev, uint32_t width, uint32_t height, uint32_t nc,
                                  const zj_output_desc *d, void *dst_dev, size_t dst_len);
 /* zj_gpu_reconstruct_device followed by the consumer: out_dev[i] receives zj_consumer_output_size(&imgs[i], d) bytes.  The
- * interleaved u8 intermediate lives in a stream-ordered scratch buffer and is produced and consumed sub-batch by sub-batch,
- * sized to stay inside the L2 cache between the two kernels.  Returns after `stream` has drained. */
+ * interleaved u8 intermediate lives in a stream-ordered scratch buffer and is produced and consumed in sub-batches of at most
+ * ZJ_CONSUMER_CHUNK_MB megabytes (default 1024).  Returns after `stream` has drained. */
 ZJ_API int zj_gpu_reconstruct_device_ex(int device, void *stream, const zj_image *imgs, size_t n, const zj_output_desc *d,
                                         void *const *out_dev, const size_t *out_len);
 
@@ -285,6 +285,13 @@ ZJ_API size_t zj_decoder_entropy_segments(const zj_decoder *d);
 ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out,
                                     size_t *out_len);
 ZJ_API void zj_buffer_free(uint8_t *p);
+/* decode_into of later zune-jpeg releases: the same, into the caller's buffer of out_cap bytes (pinned memory from
+ * zj_gpu_pinned_alloc makes every copy asynchronous); *out_len = bytes written.  Baseline images of >= 4 MP run as a strip
+ * pipeline the way the reference's driver does (src/mcu.rs:230-369 entropy-decodes strip k+1 while its pool post-processes
+ * strip k): finished strip ranges (zj_image_strip_range) are uploaded, reconstructed and downloaded while the host --
+ * sequentially, or with its restart intervals side by side -- is still entropy-decoding the rest of the image. */
+ZJ_API int zj_decoder_decode_into(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t *out, size_t out_cap,
+                                  size_t *out_len);
 /* Batch front door (the reference has none: it parallelises the strips of ONE image, mcu.rs:230-369): n JPEGs are
  * decoded by `o->num_threads` host threads (0 = one per hardware thread), one image per thread at a time; each thread
  * runs the host stage, hands its planes to zj_gpu_reconstruct_submit and starts on its next image (a second set of planes)

@@ -86,8 +86,16 @@ def test_reconstruct_device_ex_matches_spec(layout, dtype, half, channels):
 
 
 @pytest.mark.gpu
-def test_consumer_sub_batches(monkeypatch):
-    """More images than one L2-sized sub-batch holds: every sub-batch reuses the same scratch buffer."""
+def test_consumer_sub_batches():
+    """More images than one sub-batch holds (ZJ_CONSUMER_CHUNK_MB): every sub-batch reuses the same scratch buffer."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("ZJ_CONSUMER_CHUNK_MB") != "48":      # the budget is read once per process: run this test in a child
+        env = dict(os.environ, ZJ_CONSUMER_CHUNK_MB="48")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__ + "::test_consumer_sub_batches"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
     from zune_jpeg_b200 import gpu
     rng = np.random.default_rng(5)
     cases = [(1920, 1088, "420", 0)] * 12        # 6.3 MB of u8 each: 48 MB sub-batches hold 7

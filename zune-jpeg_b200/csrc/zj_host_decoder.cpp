@@ -514,34 +514,55 @@ struct Component {  // src/components.rs:18-43
     uint8_t id;
 };
 
-struct PlaneBuf {
-    int16_t *p = nullptr;
+// The three coefficient planes of an image live in ONE block (pinned when a device is present), each plane on a 256-byte
+// boundary: zj_gpu_reconstruct uploads planes that follow each other in host memory with a single copy (three copies of
+// 16.6 + 4.1 + 4.1 MB for a 4K 4:2:0 image run at 44 GB/s over PCIe, one of 24.9 MB at 49).
+struct PlaneBuf { int16_t *p = nullptr; };
+struct PlaneBlock {
+    int16_t *base = nullptr;
     size_t cap = 0;   // i16
     bool pinned = false;
     void release()
     {
-        if (!p) return;
-        if (pinned) cudaFreeHost(p); else free(p);
-        p = nullptr; cap = 0;
+        if (!base) return;
+        if (pinned) cudaFreeHost(base); else free(base);
+        base = nullptr; cap = 0;
     }
-    int16_t *ensure_zeroed(size_t n, bool want_pinned, bool zero = true)
+    // planes[z].p for plane_len[z] i16 each (0 = no plane); zeroed on request
+    void ensure(PlaneBuf (&planes)[3], const size_t (&plane_len)[3], bool want_pinned, bool zero)
     {
-        if (n > cap) {
+        size_t off[3], total = 0;
+        for (int z = 0; z < 3; z++) { off[z] = total; total += (plane_len[z] + 127) & ~(size_t)127; }
+        if (total > cap) {
             release();
-            size_t want = n + n / 8 + 64;
-            if (want_pinned && cudaHostAlloc((void **)&p, want * 2, cudaHostAllocPortable) == cudaSuccess) pinned = true;
-            else { cudaGetLastError(); p = (int16_t *)aligned_alloc(64, (want * 2 + 63) & ~(size_t)63); pinned = false; }
-            if (!p) FAIL(ZJ_DE_FORMAT, "out of memory for coefficient planes");
+            const size_t want = total + total / 8 + 128;
+            if (want_pinned && cudaHostAlloc((void **)&base, want * 2, cudaHostAllocPortable) == cudaSuccess) pinned = true;
+            else { cudaGetLastError(); base = (int16_t *)aligned_alloc(256, (want * 2 + 255) & ~(size_t)255); pinned = false; }
+            if (!base) { cap = 0; FAIL(ZJ_DE_FORMAT, "out of memory for coefficient planes"); }
             cap = want;
         }
-        if (zero) memset(p, 0, n * 2);
-        return p;
+        for (int z = 0; z < 3; z++) {
+            planes[z].p = plane_len[z] ? base + off[z] : nullptr;
+            if (zero && plane_len[z]) memset(planes[z].p, 0, plane_len[z] * 2);
+        }
     }
 };
 
 }  // namespace
 
+// Progress of the baseline entropy stage, strip by strip (the reference entropy-decodes strip k+1 while its
+// thread pool post-processes strip k, mcu.rs:230-369 / 356-368).  `begin` is called once the planes exist and the descriptor is
+// final, `progress(n)` whenever strips [0, n) of every plane are complete and will not be touched again, `restart` when the
+// planes are about to be decoded again from the start (the interval-parallel form was turned down).
+struct StripSink {
+    virtual void begin(const zj_image &img, size_t n_strips) = 0;
+    virtual void progress(size_t strips_done) = 0;
+    virtual void restart() = 0;
+    virtual ~StripSink() {}
+};
+
 struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
+    StripSink *sink = nullptr;   // set for the duration of one zj_decoder_decode_into call
     zj_options options;
     zj_image_info info{};
     bool qt_present[4] = {false, false, false, false};
@@ -561,6 +582,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
     std::string err_msg, err_display;
     // coefficient planes (reused across calls)
     PlaneBuf planes[3];
+    PlaneBlock plane_block;
     size_t plane_len[3] = {0, 0, 0};
     bool have_device = false;
     // restart-interval-parallel entropy decode: threads to use (0 = options.num_threads) and how many intervals the last
@@ -575,7 +597,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         have_device = cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
         if (!have_device) cudaGetLastError();
     }
-    ~zj_decoder() { for (auto &p : planes) p.release(); }
+    ~zj_decoder() { plane_block.release(); }
 
     void reset_state()  // a fresh Decoder::default(options) for every call, keeping the plane buffers
     {
@@ -897,6 +919,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         const size_t per_strip = g.bias * g.mcu_w;
         for (size_t m = first; m < last; m++) {
             const size_t strip = m / per_strip, v = (m - strip * per_strip) / g.mcu_w, j = m - strip * per_strip - v * g.mcu_w;
+            if (!SEGMENT && sink && strip > 0 && m == strip * per_strip) sink->progress(strip);
             if (!SEGMENT && g.zero_per_strip && m == strip * per_strip) {
                 // the planes start out zeroed (mcu.rs:238-250 allocates fresh zeroed strip buffers): done strip by strip right
                 // before the strip is decoded, so the blocks are still in cache when the coefficients are written
@@ -1000,6 +1023,20 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         if (threads > n_seg) threads = n_seg;
         std::atomic<size_t> next{0};
         std::atomic<bool> bad{false};
+        // strips complete so far = the prefix of finished intervals (intervals are claimed in order, so the prefix keeps up)
+        std::mutex prefix_mu;
+        std::vector<uint8_t> seg_done(sink ? n_seg : 0, 0);
+        size_t prefix = 0, told = 0;
+        const size_t per_strip = g.bias * g.mcu_w;
+        auto finished = [&](size_t k) {
+            if (!sink) return;
+            std::lock_guard<std::mutex> lock(prefix_mu);
+            seg_done[k] = 1;
+            while (prefix < n_seg && seg_done[prefix]) prefix++;
+            if (bad.load(std::memory_order_relaxed)) return;
+            const size_t strips = std::min(total, prefix * per_seg) / per_strip;
+            if (strips > told && strips < g.mcu_h) { told = strips; sink->progress(strips); }   // (the last strip is reported by the caller)
+        };
         auto work = [&]() {
             for (;;) {
                 const size_t k = next.fetch_add(1);
@@ -1013,6 +1050,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
                 try {
                     const bool was_reset = baseline_mcus<true>(rd, st, g, first, last, must_reset);
                     if (must_reset && (!was_reset || rd.pos != ends[k])) bad = true;
+                    else finished(k);
                 } catch (SegmentAbnormal &) { bad = true; }
                 catch (...) { bad = true; }   // a DecodeError: the sequential loop will raise it at the right place
             }
@@ -1087,8 +1125,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         size_t threads = entropy_threads ? entropy_threads : (options.num_threads ? options.num_threads : std::thread::hardware_concurrency());
         if (threads == 0) threads = 1;
         const size_t total = g.mcu_w * g.mcu_h * g.bias;
-        for (size_t pos = 0; pos < 3; pos++)
-            if (plane_len[pos]) planes[pos].ensure_zeroed(plane_len[pos], have_device, false);
+        plane_block.ensure(planes, plane_len, have_device, false);
         // zeroing all planes at once, for the interval-parallel form (whose intervals start anywhere inside a strip): split over
         // the threads too -- 200 MB of planes of an 8192^2 image take as long to clear as to entropy-decode on 8 threads
         auto zero_planes = [&]() {
@@ -1103,6 +1140,11 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             work();
             for (auto &t : pool) t.join();
         };
+        if (sink) {
+            zj_image img;
+            fill_descriptor(&img);
+            sink->begin(img, g.mcu_h);
+        }
         ScanState st;
         for (size_t pos = 0; pos < g.ncomp && pos < 3; pos++) st.dc_pred[pos] = components[pos].dc_pred;
         st.todo = todo;
@@ -1112,6 +1154,7 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
             zero_planes();
             if (baseline_parallel(reader, st, g, threads)) return;
             // some interval did not end like a conformant one: the reference's loop decides what comes out
+            if (sink) sink->restart();
         }
         g.zero_per_strip = true;
         baseline_mcus<false>(reader, st, g, 0, total, false);
@@ -1273,10 +1316,8 @@ struct zj_decoder {  // Decoder, reference src/decoder.rs:60-121
         mw *= 64;
         if (components.size() < in_components()) FAIL(ZJ_DE_FORMAT, "missing components");
         for (size_t i = 0; i < 3; i++) plane_len[i] = 0;
-        for (size_t i = 0; i < in_components(); i++) {
-            plane_len[i] = mw * components[i].vertical_sample * components[i].horizontal_sample * mh;
-            planes[i].ensure_zeroed(plane_len[i], have_device);
-        }
+        for (size_t i = 0; i < in_components(); i++) plane_len[i] = mw * components[i].vertical_sample * components[i].horizontal_sample * mh;
+        plane_block.ensure(planes, plane_len, have_device, true);
         size_t seen_scans = 1;
         BitStream stream;
         stream.update_progressive_params(succ_high, succ_low, spec_start, spec_end);
@@ -1418,27 +1459,127 @@ ZJ_API int zj_decoder_decode_coefficients(zj_decoder *d, const uint8_t *buf, siz
     return ZJ_OK;
 }
 
-ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out, size_t *out_len)
+// Strip pipeline of ONE image (mcu.rs:230-369): finished strip ranges are uploaded, reconstructed and downloaded
+// while the host is still entropy-decoding the rest of the same image.  Ranges are the virtual images of zj_image_strip_range,
+// queued with zj_gpu_reconstruct_submit on the calling thread's cached streams; one finish per range at the end.
+struct PipeSink : StripSink {
+    int device = 0;
+    uint8_t *out = nullptr;
+    size_t out_cap = 0;
+    zj_image img{};
+    size_t n_strips = 0, step = 0, submitted = 0;
+    std::vector<zj_pending *> pend;
+    std::mutex mu;
+    int rc = ZJ_OK;
+    bool active = false;
+    void begin(const zj_image &im, size_t ns) override
+    {
+        img = im;
+        uint32_t plan_strips = 0;
+        // only when the image plans, has as many strips as the host stage counts, and is worth cutting
+        if (zj_image_strip_range(&img, 0, 0, nullptr, nullptr, nullptr, &plan_strips) != ZJ_OK || plan_strips != ns) return;
+        if (zj_output_size(&img) == 0 || zj_output_size(&img) > out_cap) return;
+        static const size_t ranges = [] { const char *e = getenv("ZJ_STRIP_RANGES"); long v = e ? atol(e) : 8; return (size_t)(v < 1 ? 1 : v); }();
+        static const size_t min_px = [] { const char *e = getenv("ZJ_STRIP_PIPE_MIN_MP"); double v = e ? atof(e) : 4.0; return (size_t)(v * 1e6); }();
+        if (ranges < 2 || (size_t)img.width * img.height < min_px || ns < 2 * ranges) return;
+        n_strips = ns;
+        step = (ns + ranges - 1) / ranges;
+        active = true;
+    }
+    void submit_range(size_t s0, size_t s1)
+    {
+        zj_image sub;
+        size_t off = 0, bytes = 0;
+        int r = zj_image_strip_range(&img, (uint32_t)s0, (uint32_t)s1, &sub, &off, &bytes, nullptr);
+        if (r == ZJ_OK && bytes) {
+            uint8_t *o = out + off;
+            zj_pending *pd = nullptr;
+            r = zj_gpu_reconstruct_submit(device, nullptr, &sub, 1, &o, &bytes, &pd);
+            if (r == ZJ_OK) pend.push_back(pd);
+        }
+        if (r != ZJ_OK && rc == ZJ_OK) rc = r;
+    }
+    void progress(size_t done) override
+    {
+        if (!active) return;
+        std::lock_guard<std::mutex> lock(mu);
+        while (rc == ZJ_OK && submitted + step <= done && submitted + step < n_strips) {
+            submit_range(submitted, submitted + step);
+            submitted += step;
+        }
+    }
+    int drain()
+    {
+        int r = rc;
+        for (zj_pending *pd : pend) { const int f = zj_gpu_reconstruct_finish(pd); if (f != ZJ_OK && r == ZJ_OK) r = f; }
+        pend.clear();
+        return r;
+    }
+    void restart() override
+    {
+        if (!active) return;
+        std::lock_guard<std::mutex> lock(mu);
+        drain();            // (copies of the first attempt may still be reading the planes)
+        rc = ZJ_OK;
+        submitted = 0;
+    }
+    // the entropy stage is done: the remaining strips (and the rows below them), then wait for everything
+    int finish()
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (rc == ZJ_OK) submit_range(submitted, n_strips);
+        submitted = n_strips;
+        return drain();
+    }
+    ~PipeSink() override { drain(); }
+};
+
+// decode_into of later zune-jpeg releases (BASELINE north_star names `decode()/decode_into()`): the pixels go into the caller's
+// buffer (pinned memory makes every copy asynchronous).  Baseline images of some size run the strip pipeline above.
+ZJ_API int zj_decoder_decode_into(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t *out, size_t out_cap, size_t *out_len)
 {
     if (!d || (!buf && len) || !out || !out_len) return ZJ_ERR_INVALID_ARG;
-    *out = nullptr;
     *out_len = 0;
+    PipeSink ps;
+    ps.device = d->options.device;
+    ps.out = out;
+    ps.out_cap = out_cap;
     zj_image img;
+    d->sink = d->have_device ? &ps : nullptr;
     int rc = zj_decoder_decode_coefficients(d, buf, len, &img);
-    if (rc) return rc;
+    d->sink = nullptr;
+    if (rc) return rc;          // (~PipeSink waits for whatever was queued)
     const size_t n = zj_output_size(&img);
     rc = zj_validate_image(&img);
     if (rc == ZJ_OK && n == 0) rc = ZJ_ERR_INVALID_ARG;
-    uint8_t *o = nullptr;
-    if (rc == ZJ_OK) { o = (uint8_t *)malloc(n ? n : 1); if (!o) rc = ZJ_ERR_OOM; }
-    if (rc == ZJ_OK) rc = zj_gpu_reconstruct(d->options.device, nullptr, &img, 1, &o, &n);
+    if (rc == ZJ_OK && n > out_cap) rc = ZJ_ERR_SHORT_OUTPUT;
+    if (rc == ZJ_OK) rc = ps.active ? ps.finish() : zj_gpu_reconstruct(d->options.device, nullptr, &img, 1, &out, &n);
     if (rc != ZJ_OK) {
-        free(o);
         std::string m = zj_gpu_strerror(rc);
         if (rc == ZJ_ERR_CUDA || rc == ZJ_ERR_OOM) m += std::string(" -- ") + zj_gpu_last_cuda_error();
         d->set_error(DecodeError{rc == ZJ_ERR_UNSUPPORTED ? ZJ_DE_FORMAT : ZJ_DE_GPU, m});
         return rc;
     }
+    *out_len = n;
+    return ZJ_OK;
+}
+
+ZJ_API int zj_decoder_decode_buffer(zj_decoder *d, const uint8_t *buf, size_t len, uint8_t **out, size_t *out_len)
+{
+    if (!d || (!buf && len) || !out || !out_len) return ZJ_ERR_INVALID_ARG;
+    *out = nullptr;
+    *out_len = 0;
+    // the size comes from the headers (mcu.rs:375-379: width * height * out components); they are parsed again by the decode
+    int rc = zj_decoder_read_headers(d, buf, len);
+    if (rc) return rc;
+    const uint32_t cs = d->options.out_colorspace;
+    const size_t nc = cs == ZJ_CS_GRAYSCALE ? 1 : ((cs == ZJ_CS_RGB || cs == ZJ_CS_YCBCR) ? 3 : 4);
+    const size_t cap = (size_t)d->info.width * d->info.height * nc;
+    uint8_t *o = (uint8_t *)malloc(cap ? cap : 1);
+    if (!o) return ZJ_ERR_OOM;
+    size_t n = 0;
+    rc = zj_decoder_decode_into(d, buf, len, o, cap, &n);
+    if (rc != ZJ_OK) { free(o); return rc; }
     *out = o;
     *out_len = n;
     return ZJ_OK;

@@ -188,6 +188,21 @@ class Decoder:
 
     decode = decode_buffer  # name used by later zune-jpeg releases
 
+    def decode_into(self, buf, out) -> int:
+        """JpegDecoder::decode_into of later zune-jpeg releases: the pixels go into `out` (a writable uint8 buffer, e.g. a
+        PinnedBuffer.array slice); returns the number of bytes written.  Baseline images of >= 4 MP run as a strip pipeline
+        (zj_decoder_decode_into): finished strip ranges are on their way through the GPU while the host still entropy-decodes."""
+        import numpy as np
+        data = buf if isinstance(buf, np.ndarray) else bytes(buf)
+        p = data.ctypes.data if isinstance(data, np.ndarray) else C.cast(C.c_char_p(data), C.c_void_p).value
+        n_in = data.nbytes if isinstance(data, np.ndarray) else len(data)
+        view = out if isinstance(out, np.ndarray) else np.frombuffer(out, dtype=np.uint8)
+        n = C.c_size_t()
+        rc = self._lib.zj_decoder_decode_into(self._h, p, n_in, view.ctypes.data, view.nbytes, C.byref(n))
+        if rc != 0:
+            self._raise(rc)
+        return int(n.value)
+
     def decode_file(self, path) -> bytes:
         """Decoder::decode_file (decoder.rs:193)"""
         try:
