@@ -18,7 +18,7 @@ def _expect(data, out_cs=0):
 
 
 @pytest.mark.parametrize("sub,rst,threads", [("420", 0, 1), ("420", 1, 8), ("422", 2, 8), ("444", 1, 4), ("420", 1, 1)])
-def test_decode_into_pipeline_matches_oracle(sub, rst, threads, monkeypatch):
+def test_decode_into_pipeline_matches_oracle(sub, rst, threads):
     from zune_jpeg_b200 import gpu
     from zune_jpeg_b200.decoder import ColorSpace, Decoder, ZuneJpegOptions
     w, h = 2560, 1723                    # 4.4 MP: above the pipeline's threshold; odd height (partial last strip)

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -637,6 +638,10 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
         rc = check_buffers(&imgs[i], plans[i], out[i], out_len[i]);
         if (rc) return rc;
     }
+    static const bool trace = getenv("ZJ_SUBMIT_TRACE") != nullptr;
+    auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_in = trace ? now_ms() : 0;
+    auto lap = [&](const char *what) { if (trace) fprintf(stderr, "[zj submit] %-22s +%.3f ms\n", what, now_ms() - t_in); };
     cudaStream_t user = (cudaStream_t)stream;
     constexpr int NS_MAX = 4;
     const char *env_ns = getenv("ZJ_E2E_STREAMS"), *env_mb = getenv("ZJ_E2E_BUDGET_MB");
@@ -678,6 +683,7 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
     CU(cudaEventRecord(ev_in, user));
     for (int k = 0; k < NS; k++) CU(cudaStreamWaitEvent(st[k], ev_in, 0));
     cudaEventDestroy(ev_in);   // (released once the recorded work has completed)
+    lap("streams + entry event");
 
     zj_pending *pd = new (std::nothrow) zj_pending;
     if (!pd) return ZJ_ERR_OOM;
@@ -725,6 +731,7 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
             if (e != cudaSuccess) { cache.buf[device][slot] = nullptr; rc = cuda_fail(e, "cudaMalloc(staging)"); break; }
             cache.cap[device][slot] = bytes + bytes / 8;
         }
+        lap("staging buffer");
         uint8_t *pool = cache.buf[device][slot];
         std::vector<zj_image> dimgs(imgs + i, imgs + j);
         std::vector<uint8_t *> douts(j - i);
@@ -742,9 +749,8 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
             const uint32_t nz = plans[k].ncomp_used;
             size_t nbz[3] = {0, 0, 0}, rel[3] = {0, 0, 0}, sum = 0;
             bool merge = nz > 1;
+            for (uint32_t z = 0; z < nz; z++) { nbz[z] = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2; sum += nbz[z]; }
             for (uint32_t z = 0; z < nz; z++) {
-                nbz[z] = (size_t)plans[k].n_strips * plans[k].chunk[z] * 2;
-                sum += nbz[z];
                 const uintptr_t a0 = reinterpret_cast<uintptr_t>(imgs[k].comp[0].coeff), az = reinterpret_cast<uintptr_t>(imgs[k].comp[z].coeff);
                 if (az < a0) { merge = false; break; }
                 rel[z] = az - a0;
@@ -777,6 +783,7 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
             }
         }
         if (rc != ZJ_OK) { zj_batch_destroy(b); break; }
+        lap("descriptors + uploads");
         pd->batches.push_back(b);
         if (pipe) { CUB(cudaEventRecord(cache.ev[device][slot][0], s_up)); CUB(cudaStreamWaitEvent(s_k, cache.ev[device][slot][0], 0)); }
         rc = zj_batch_run(b, s_k);
@@ -787,6 +794,7 @@ int zj_gpu_reconstruct_submit(int device, void *stream, const zj_image *imgs, si
             if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
         }
         if (pipe && rc == ZJ_OK) { CUB(cudaEventRecord(cache.ev[device][slot][2], s_dn)); cache.ev_rec[device][slot] = true; }
+        lap("kernels + downloads");
         i = j;
     }
     if (rc == ZJ_OK) {

@@ -1479,15 +1479,24 @@ struct PipeSink : StripSink {
         // only when the image plans, has as many strips as the host stage counts, and is worth cutting
         if (zj_image_strip_range(&img, 0, 0, nullptr, nullptr, nullptr, &plan_strips) != ZJ_OK || plan_strips != ns) return;
         if (zj_output_size(&img) == 0 || zj_output_size(&img) > out_cap) return;
-        static const size_t ranges = [] { const char *e = getenv("ZJ_STRIP_RANGES"); long v = e ? atol(e) : 8; return (size_t)(v < 1 ? 1 : v); }();
+        // a pageable destination makes every download a blocking, staged copy on the thread that queues it (2 GB/s): such
+        // callers get the one-shot path, whose single download at least waits for nothing else
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); return; }
+        static const size_t ranges = [] { const char *e = getenv("ZJ_STRIP_RANGES"); long v = e ? atol(e) : 16; return (size_t)(v < 1 ? 1 : v); }();
         static const size_t min_px = [] { const char *e = getenv("ZJ_STRIP_PIPE_MIN_MP"); double v = e ? atof(e) : 4.0; return (size_t)(v * 1e6); }();
         if (ranges < 2 || (size_t)img.width * img.height < min_px || ns < 2 * ranges) return;
         n_strips = ns;
         step = (ns + ranges - 1) / ranges;
         active = true;
+        t_begin = now_ms();
     }
+    static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    double t_begin = 0;
     void submit_range(size_t s0, size_t s1)
     {
+        static const bool trace = getenv("ZJ_PIPE_TRACE") != nullptr;
+        const double t0 = trace ? now_ms() : 0;
         zj_image sub;
         size_t off = 0, bytes = 0;
         int r = zj_image_strip_range(&img, (uint32_t)s0, (uint32_t)s1, &sub, &off, &bytes, nullptr);
@@ -1498,6 +1507,7 @@ struct PipeSink : StripSink {
             if (r == ZJ_OK) pend.push_back(pd);
         }
         if (r != ZJ_OK && rc == ZJ_OK) rc = r;
+        if (trace) fprintf(stderr, "[zj pipe] strips [%zu, %zu) queued at %.2f ms, submit took %.2f ms (rc %d)\n", s0, s1, t0 - t_begin, now_ms() - t0, r);
     }
     void progress(size_t done) override
     {
@@ -1529,7 +1539,9 @@ struct PipeSink : StripSink {
         std::lock_guard<std::mutex> lock(mu);
         if (rc == ZJ_OK) submit_range(submitted, n_strips);
         submitted = n_strips;
-        return drain();
+        const int r = drain();
+        if (getenv("ZJ_PIPE_TRACE")) fprintf(stderr, "[zj pipe] drained at %.2f ms\n", now_ms() - t_begin);
+        return r;
     }
     ~PipeSink() override { drain(); }
 };
@@ -1546,8 +1558,11 @@ ZJ_API int zj_decoder_decode_into(zj_decoder *d, const uint8_t *buf, size_t len,
     ps.out_cap = out_cap;
     zj_image img;
     d->sink = d->have_device ? &ps : nullptr;
+    const bool trace = getenv("ZJ_PIPE_TRACE") != nullptr;
+    const double t_call = trace ? PipeSink::now_ms() : 0;
     int rc = zj_decoder_decode_coefficients(d, buf, len, &img);
     d->sink = nullptr;
+    if (trace) fprintf(stderr, "[zj pipe] host stage returned after %.2f ms (begin was at +%.2f ms)\n", PipeSink::now_ms() - t_call, ps.t_begin - t_call);
     if (rc) return rc;          // (~PipeSink waits for whatever was queued)
     const size_t n = zj_output_size(&img);
     rc = zj_validate_image(&img);

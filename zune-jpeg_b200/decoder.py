@@ -212,15 +212,6 @@ class Decoder:
             raise DecodeErrors(1, f"Error decoding an image:\n {e}")
         return self.decode_buffer(data)
 
-    def decode_into(self, buf: bytes, out) -> int:
-        """Alias in the spirit of later releases: decode into a caller buffer, returns bytes written."""
-        px = self.decode_buffer(buf)
-        mv = memoryview(out).cast("B")
-        if len(mv) < len(px):
-            raise DecodeErrors(1, "output buffer too small")
-        mv[: len(px)] = px
-        return len(px)
-
     def read_headers(self, buf: bytes) -> None:
         """Decoder::read_headers (decoder.rs:452)"""
         buf = bytes(buf)
