@@ -334,6 +334,55 @@ def test_baseline_configs_from_jpeg_bytes(name, w, h, sub, prog, gray, out_cs, r
     assert (d.entropy_segments() > 0) == bool(rst)
 
 
+def test_c2_from_jpeg_bytes_all_bench_images():
+    """BASELINE configs[1] from JPEG bytes: the eight distinct 3840x2160 4:2:0 images bench.py cycles through its batch of 256
+    (same seeds, quality 90), decoded by decode_batch (host stage + GPU) and checked against the oracle -- all eight, not
+    only the first one the bench itself checks."""
+    import os
+    import jpeg_util
+    from zune_jpeg_b200.decoder import ColorSpace, Decoder, ZuneJpegOptions, decode_batch
+    opts = ZuneJpegOptions().set_out_colorspace(ColorSpace.RGB)
+    datas = [jpeg_util.synth_jpeg(i, 3840, 2160, "420", 90) for i in range(8)]      # bench.make_pool: seed = 1000 * rank + i
+    got = decode_batch(datas, opts, threads=8)
+    for data, g in zip(datas, got):
+        img, planes = Decoder.new_with_options(opts.set_num_threads(1)).decode_coefficients(data)
+        want = oracle.reconstruct(img, threads=os.cpu_count() or 1)
+        assert isinstance(g, bytes) and len(g) == 3840 * 2160 * 3
+        assert np.array_equal(np.frombuffer(g, np.uint8), want)
+
+
+def test_mixed_geometry_batch_launch_groups():
+    """A heterogeneous device-resident batch: images are grouped by kernel (luma-only / fast / mode / variant), one launch per
+    group, and a group's grid is sized by its LARGEST member -- a 4000-wide and an 80-wide image in one group (very different tile
+    counts), several modes, both variants, a luma-only output.  zj_batch_launches must equal the number of groups."""
+    from zune_jpeg_b200 import gpu
+    rng = np.random.default_rng(77)
+    cases = [(4000, 64, "420", 0, 0), (80, 400, "420", 0, 0), (640, 480, "420", 0, 0),       # one group: HV fast, 1 .. 16 tiles, 2 .. 15 strips
+             (333, 100, "444", 0, 0), (1000, 96, "422", 5, 0),                                 # NONE fast, H fast
+             (200, 64, "420", 0, 1), (264, 100, "440", 2, 1),                                   # SCALAR variant: generic kernels (HV, V)
+             (520, 90, "420", 1, 0), (72, 40, "444", 1, 0)]                                     # luma-only output: gray fast kernel, two modes
+    imgs, wants, outs, keep = [], [], [], []
+    for (w, h, mode, out_cs, variant) in cases:
+        hs, vs = MODES[mode]
+        planes = util.random_planes(rng, w, h, 3, hs, vs)
+        wants.append(oracle.reconstruct(util.make_image(w, h, planes, QTS, hs, vs, out_cs, variant)))
+        bufs = [gpu.DeviceBuffer(p.nbytes) for p in planes]
+        for b, p in zip(bufs, planes):
+            b.upload(p)
+        o = gpu.DeviceBuffer(len(wants[-1]))
+        o.memset(0x5A)
+        keep.append((planes, bufs))
+        outs.append(o)
+        imgs.append(util.make_image(w, h, planes, QTS, hs, vs, out_cs, variant, ptrs=[b.ptr for b in bufs]))
+    batch = gpu.Batch(imgs, [o.ptr for o in outs], [len(w_) for w_ in wants])
+    assert batch.launches == 7          # HV fast | NONE fast | H fast | HV generic SCALAR | V generic SCALAR | gray HV | gray NONE
+    before = gpu.launch_count()
+    batch.run()
+    assert gpu.launch_count() - before == 7
+    for (case, o, want) in zip(cases, outs, wants):
+        assert np.array_equal(o.download(), want), case
+
+
 def test_gpu_entropy_decode_matches_host_stage():
     """zj_decode_batch_gpu: restart intervals entropy-decoded one per GPU thread (zj_entropy.cu) give the pixels of the host
     stage (the reference's sequential loop); images without restart markers, progressive ones, streams whose declared DRI does
