@@ -300,6 +300,11 @@ ZJ_API int zj_decoder_decode_into(zj_decoder *d, const uint8_t *buf, size_t len,
  * images (0 = all decoded) or a negative zj_status for invalid arguments. */
 ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                            uint8_t **out, size_t *out_len, int *status);
+/* The DecodeErrors of image i of the LAST batch call made by the calling thread (any of the zj_decode_batch* front doors):
+ * the variant (zj_decode_error_kind) and Display text Decoder::decode_buffer would have reported for that input
+ * (src/errors.rs:16-113); ZJ_DE_NONE / "" for images that decoded.  Valid until the thread's next batch call. */
+ZJ_API int zj_batch_error_kind(size_t i);
+ZJ_API const char *zj_batch_error(size_t i);
 /* zj_decode_batch keeps its workers' decoders (pinned coefficient planes sized for the largest image seen, two per host
  * thread) for the next call; this frees them. */
 /* zj_decode_batch over several devices of one box: contiguous image ranges, one per device, each range decoded by its own

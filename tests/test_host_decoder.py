@@ -167,3 +167,19 @@ def test_decode_batch_without_a_device():
     assert res[0].status == -6 and res[2].status == -6      # ZJ_ERR_NO_DEVICE
     assert res[1].status == -9                                # ZJ_ERR_DECODE
     assert decode_batch([]) == []
+
+
+def test_decode_batch_reports_the_references_error_per_image():
+    """The batch front doors carry the reference's DecodeErrors per image (zj_batch_error_kind / zj_batch_error): the same
+    variant and message Decoder.decode_buffer raises for that input -- the inputs of the reference's tests/invalid_images.rs.
+    (No device needed: these inputs fail in the host stage.)"""
+    from zune_jpeg_b200.decoder import decode_batch
+    bad = [bytes([0xff, 0xd8, 0xa4]), bytes([0xff, 0xd8, 0xff, 0x00, 0x00, 0x00]), bytes([255, 216, 255, 218, 232, 197, 255]),
+           bytes([255, 216, 255, 196, 0, 0]), bytes([255, 216, 255, 192, 255, 1, 8, 9, 119, 48, 255, 192]), b"\x89PNG\r\n"]
+    for kw in ({}, {"gpu_entropy": True}):
+        res = decode_batch(bad, threads=3, **kw)
+        for data, r in zip(bad, res):
+            with pytest.raises(DecodeErrors) as e:
+                Decoder.new().decode_buffer(data)
+            assert isinstance(r, DecodeErrors) and r.status == -9
+            assert (r.variant, r.message) == (e.value.variant, e.value.message), (data, kw)

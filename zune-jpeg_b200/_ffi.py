@@ -148,6 +148,8 @@ SYMBOLS = {
                                       C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "zj_decode_batch_gpu_device": (C.c_int, [C.POINTER(ZjOptions), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_size_t,
                                              C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "zj_batch_error_kind": (C.c_int, [C.c_size_t]),
+    "zj_batch_error": (C.c_char_p, [C.c_size_t]),
     "zj_release_host_caches": (None, []),
     "zj_release_device_caches": (None, []),
     "zj_host_set_quirks": (None, [C.c_uint32]),

@@ -1619,8 +1619,30 @@ ZJ_API void zj_release_host_caches(void)
 // stage of DIFFERENT images side by side: every worker owns a decoder (its pinned coefficient planes are reused from
 // image to image), entropy-decodes one image, hands the planes to zj_gpu_reconstruct on its own streams and moves on,
 // so the Huffman stage of some images overlaps transfer and reconstruction of others.
+// DecodeErrors of the images of the last batch call of this thread (zj_batch_error_kind / zj_batch_error): the batch front
+// doors report a per-image zj_status; the variant and Display text the reference's Decoder would have returned live here.
+struct BatchErr { int kind = ZJ_DE_NONE; std::string msg; };
+static thread_local std::vector<BatchErr> t_batch_err;
+static void note_gpu_error(BatchErr *e, int rc)
+{
+    if (!e || rc == ZJ_OK) return;
+    e->kind = rc == ZJ_ERR_UNSUPPORTED ? ZJ_DE_FORMAT : ZJ_DE_GPU;
+    e->msg = zj_gpu_strerror(rc);
+}
+static int decode_batch_impl(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                             uint8_t **out, size_t *out_len, int *status, BatchErr *errs);
+
 ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
                            uint8_t **out, size_t *out_len, int *status)
+{
+    try { t_batch_err.assign(n, BatchErr{}); } catch (...) { return ZJ_ERR_OOM; }
+    return decode_batch_impl(o, bufs, lens, n, out, out_len, status, t_batch_err.data());
+}
+ZJ_API int zj_batch_error_kind(size_t i) { return i < t_batch_err.size() ? t_batch_err[i].kind : (int)ZJ_DE_NONE; }
+ZJ_API const char *zj_batch_error(size_t i) { return i < t_batch_err.size() ? t_batch_err[i].msg.c_str() : ""; }
+
+static int decode_batch_impl(const zj_options *o, const uint8_t *const *bufs, const size_t *lens, size_t n,
+                             uint8_t **out, size_t *out_len, int *status, BatchErr *errs)
 {
     if ((!bufs || !lens || !out || !out_len || !status) && n) return ZJ_ERR_INVALID_ARG;
     zj_options opt;
@@ -1664,7 +1686,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
             const int rc = zj_gpu_reconstruct_finish(fl.pd);
             fl.pd = nullptr;
             if (rc == ZJ_OK) { out[fl.i] = fl.dst; out_len[fl.i] = fl.need; }
-            else { if (fl.mine) free(fl.dst); if (fl.mine || !out[fl.i]) out[fl.i] = nullptr; out_len[fl.i] = 0; failed++; }
+            else { if (fl.mine) free(fl.dst); if (fl.mine || !out[fl.i]) out[fl.i] = nullptr; out_len[fl.i] = 0; failed++; note_gpu_error(errs ? errs + fl.i : nullptr, rc); }
             status[fl.i] = rc;
         };
         int cur = 0;
@@ -1673,9 +1695,10 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
             if (i >= n) break;
             if (!dec[cur]) dec[cur] = take_decoder();
             zj_decoder *d = dec[cur];
-            if (!d) { status[i] = ZJ_ERR_OOM; out_len[i] = 0; failed++; continue; }
+            if (!d) { status[i] = ZJ_ERR_OOM; out_len[i] = 0; failed++; note_gpu_error(errs ? errs + i : nullptr, ZJ_ERR_OOM); continue; }
             zj_image img;
             int rc = (!bufs[i] && lens[i]) ? ZJ_ERR_INVALID_ARG : zj_decoder_decode_coefficients(d, bufs[i], lens[i], &img);
+            if (rc == ZJ_ERR_DECODE && errs) { errs[i].kind = d->err_kind; errs[i].msg = d->err_display; }   // the reference's DecodeErrors
             size_t need = 0;
             if (rc == ZJ_OK) {
                 need = zj_output_size(&img);
@@ -1700,6 +1723,7 @@ ZJ_API int zj_decode_batch(const zj_options *o, const uint8_t *const *bufs, cons
                 out_len[i] = 0;
                 failed++;
                 status[i] = rc;
+                if (rc != ZJ_ERR_DECODE) note_gpu_error(errs ? errs + i : nullptr, rc);
             }
         }
         settle();
@@ -1876,6 +1900,7 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     }
 
     lap("headers + marker scan", nullptr);
+    std::vector<BatchErr> batch_errs(n);
     // ---- the host route (zj_decode_batch) for a list of images.  Those that cannot use the GPU entropy stage at all (no DRI,
     // progressive, header errors) start on it right away, on the host threads, while the GPU works on the others.
     auto run_host = [&](const std::vector<size_t> &rest) -> int {
@@ -1889,10 +1914,12 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
             o2[t] = dev_out ? nullptr : out[rest[t]];          // device outputs: decoded into host memory first, then uploaded
             ol2[t] = dev_out ? 0 : out_len[rest[t]];
         }
-        int f = zj_decode_batch(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data());
+        std::vector<BatchErr> e2(rest.size());
+        int f = decode_batch_impl(&opt, b2.data(), l2.data(), rest.size(), o2.data(), ol2.data(), s2.data(), e2.data());
         if (f < 0) return f;
         for (size_t t = 0; t < rest.size(); t++) {
             const size_t i = rest[t];
+            batch_errs[i] = e2[t];
             if (!dev_out) { out[i] = o2[t]; out_len[i] = ol2[t]; status[i] = s2[t]; continue; }
             int rc = s2[t];
             if (rc == ZJ_OK) {
@@ -2130,6 +2157,8 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
     const int late_rc = run_host(rest);
     if (late_rc < 0) return late_rc;
     failed += late_rc;
+    for (size_t i = 0; i < n; i++) if (status[i] != ZJ_OK && batch_errs[i].kind == ZJ_DE_NONE) note_gpu_error(&batch_errs[i], status[i]);
+    t_batch_err.swap(batch_errs);
     return failed;
 }
 

@@ -346,7 +346,10 @@ def decode_batch(buffers, options: ZuneJpegOptions | None = None, threads: int =
     res = []
     for i in range(n):
         if status[i] != 0:
-            res.append(DecodeErrors(13 if status[i] != _ffi.ERR_DECODE else 1, lib.zj_gpu_strerror(status[i]).decode(), status[i]))
+            # the variant and text Decoder.decode_buffer raises for the same input (zj_batch_error_kind / zj_batch_error)
+            kind = lib.zj_batch_error_kind(i) if devices is None else 0
+            text = lib.zj_batch_error(i).decode(errors="replace") if kind else lib.zj_gpu_strerror(status[i]).decode()
+            res.append(DecodeErrors(kind or (13 if status[i] != _ffi.ERR_DECODE else 1), text, status[i]))
         elif out is not None or device_out is not None:
             res.append(int(out_len[i]))
         else:
