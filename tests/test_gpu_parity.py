@@ -345,7 +345,10 @@ def test_c2_from_jpeg_bytes_all_bench_images():
     datas = [jpeg_util.synth_jpeg(i, 3840, 2160, "420", 90) for i in range(8)]      # bench.make_pool: seed = 1000 * rank + i
     got = decode_batch(datas, opts, threads=8)
     for data, g in zip(datas, got):
-        img, planes = Decoder.new_with_options(opts.set_num_threads(1)).decode_coefficients(data)
+        seq = Decoder.new_with_options(opts.set_num_threads(1))
+        img, planes = seq.decode_coefficients(data)
+        for z in range(img.n_comp):                      # (the descriptor points into the decoder: re-point it at the copies)
+            img.comp[z].coeff = planes[z].ctypes.data if planes[z].size else None
         want = oracle.reconstruct(img, threads=os.cpu_count() or 1)
         assert isinstance(g, bytes) and len(g) == 3840 * 2160 * 3
         assert np.array_equal(np.frombuffer(g, np.uint8), want)

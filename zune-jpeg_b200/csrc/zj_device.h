@@ -45,7 +45,12 @@ constexpr int ZF_MINBLOCKS = ZF_CFG_MINBLOCKS;
 constexpr int ZF_DEFAULT_SPC = ZF_CFG_SPC;      // target strips per CTA (see strips_per_cta)
 // unit columns (16 luma samples) per tile: 2 * ZF_CONSUMERS / row groups per strip
 constexpr int ZF_XU_GRAY = 32;                  // luma-only fast kernel: 512-sample tiles
-constexpr int ZF_XU_NONE = 2 * ZF_CONSUMERS / 8, ZF_XU_H = 2 * ZF_CONSUMERS / 16, ZF_XU_V = 2 * ZF_CONSUMERS / 8, ZF_XU_HV = 2 * ZF_CONSUMERS / 16;
+// (4:2:2: 15 instead of 16 -- the strip-tile's block list, 2 x 30 luma + 2 x 2 x 15 chroma + 8 halo blocks, is then exactly
+// 128 = one IDCT pass of the four producer warps; with 16 it is 136 and the producers' critical path a second pass)
+#ifndef ZF_CFG_XU_H
+#define ZF_CFG_XU_H 15
+#endif
+constexpr int ZF_XU_NONE = 2 * ZF_CONSUMERS / 8, ZF_XU_H = ZF_CFG_XU_H, ZF_XU_V = 2 * ZF_CONSUMERS / 8, ZF_XU_HV = 2 * ZF_CONSUMERS / 16;
 
 struct DevImage {
     const int16_t *coeff[3];  // device pointers, whole-image planes

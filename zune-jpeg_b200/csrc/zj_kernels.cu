@@ -1132,7 +1132,8 @@ template <int MODE> struct FastTraits {
     static constexpr int CROWS = 8 * CBR;
     static constexpr int RPU = V;                     // rows per unit
     static constexpr int NRG = ROWS / RPU;            // row groups per strip
-    static constexpr int XU = 2 * ZF_CONSUMERS / NRG; // unit columns per tile (two units per consumer thread)
+    static constexpr int XU = MODE == MODE_H ? ZF_XU_H : 2 * ZF_CONSUMERS / NRG;   // unit columns per tile (two units per consumer thread; 4:2:2: see zj_device.h)
+    static_assert(XU * NRG <= 2 * ZF_CONSUMERS, "two units per consumer thread");
     static constexpr int TWY = 16 * XU;               // luma samples per tile row
     static constexpr int TWC = TWY / H;               // chroma samples per tile row
     static constexpr int YB = TWY / 8, CB = TWC / 8;  // blocks per block row of the tile
@@ -1143,6 +1144,9 @@ template <int MODE> struct FastTraits {
     static constexpr int NY = YBR * YB, NC = CBR * CB, PER = NC + NSLOT * CBR;
     static constexpr int YBYTES = ROWS * TWY, CBYTES = CROWS * CS, BUF = YBYTES + 2 * CBYTES;  // one buffer of sample planes
     static_assert(NY + 2 * PER <= 2 * ZF_PRODUCERS, "two 8x8 blocks per producer thread");
+    // block rows of 32 / 16 blocks are staged by cooperative, fully coalesced copies of whole runs; any other width packs the
+    // list densely (a job of 32 consecutive entries then spans several runs and planes) and every lane copies its own block
+    static constexpr bool DENSE = (YB % 16) != 0;
     static_assert(BUF % 16 == 0 && YBYTES % 16 == 0 && CBYTES % 8 == 0, "plane alignment");
 };
 
@@ -1371,7 +1375,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             const int lsub = lane >> 3, lch = lane & 7;
             q0[ps] = q1[ps] = im.coeff[0];
             int mode = 0, lim0 = 0, lim1 = 0;
-            if (B0 < FT::NY + 2 * FT::NC) {
+            if (FT::DENSE) {
+                if (active) { mode = 3; q0[ps] = block_ptr(comp, br, gcol); }
+            } else if (B0 < FT::NY + 2 * FT::NC) {
                 int c0, b0r, g0, l0;
                 decode(B0, c0, b0r, g0, l0);
                 const bool isY = B0 < FT::NY;
@@ -1430,7 +1436,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         // loop-carried state
         const int16_t *qa0 = q0[0], *qb0 = q1[0], *qa1 = q0[1], *qb1 = q1[1];
         const u32 pk0 = pk[0], pk1 = pk[1], jm0 = jm[0], jm1 = jm[1];
-        const u32 st0 = (wq * 32 < FT::NY) ? stepY : stepC, st1 = (ZF_PRODUCERS + wq * 32 < FT::NY) ? stepY : stepC;   // by the plane of the warp's blocks
+        // per-strip step of the copy pointers: by the plane of the warp's blocks (dense lists: of the lane's own block)
+        const u32 st0 = FT::DENSE ? ((pk0 & 0x20000u) ? stepC : stepY) : ((wq * 32 < FT::NY) ? stepY : stepC);
+        const u32 st1 = FT::DENSE ? ((pk1 & 0x20000u) ? stepC : stepY) : ((ZF_PRODUCERS + wq * 32 < FT::NY) ? stepY : stepC);
         // one staging slot per thread: the copy of the next pass is issued as soon as the row pass has drained the slot
         // and lands while the column pass runs
         const bool work0 = __any_sync(0xffffffffu, (pk0 & 0x10000u) != 0), work1 = __any_sync(0xffffffffu, (pk1 & 0x10000u) != 0);   // any block in the warp
@@ -1472,7 +1480,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     // byte 3*s, except bytes the tail chunk overwrites; the tail chunk (samples Wp-16..Wp-1) sits at T; the rest is never written
     int kind = 0;                                         // 0 = nothing to write, 1 = packed path, 2 = generic path
     int dst_off = 3 * xs, nw = 12;
-    if (u0 + xu < u1) {
+    if (u0 + xu < u1 && rgA < NRG / 2) {                   // (XU * NRG / 2 may be smaller than the consumer count: those threads idle)
         if ((u32)(xs + 16) <= n_norm) {
             kind = 1;
             if (T != 0xffffffffu && (u32)(3 * xs + 48) > T && (u32)(3 * xs) < T + 48) {   // overlaps the tail chunk's bytes [T, T+48)

@@ -220,7 +220,8 @@ class Decoder:
             self._raise(rc)
 
     def decode_coefficients(self, buf: bytes):
-        """Host stage only (headers + entropy decode): returns (zj_image descriptor, [int16 plane copies])."""
+        """Host stage only (headers + entropy decode): returns (zj_image descriptor, [int16 plane copies]); the descriptor's
+        plane pointers refer to those copies."""
         buf = bytes(buf)
         img = ZjImage()
         rc = self._lib.zj_decoder_decode_coefficients(self._h, buf, len(buf), C.byref(img))
@@ -234,6 +235,10 @@ class Decoder:
             else:
                 a = np.zeros(0, np.int16)
             planes.append(a)
+            # the descriptor is handed out pointing at the COPIES (kept alive by the descriptor object), not into the decoder's own
+            # planes, which the next decode overwrites and the decoder's destruction frees
+            c.coeff = a.ctypes.data if a.size else None
+        img._planes = planes
         return img, planes
 
     def entropy_segments(self) -> int:
