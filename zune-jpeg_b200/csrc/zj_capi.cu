@@ -223,26 +223,51 @@ struct zj_batch {
     bool pooled;
 };
 
+// Stream-ordered allocations of this library (descriptor arrays, the consumers' scratch) come from a PRIVATE memory pool per
+// device whose release threshold keeps its memory across synchronisations -- by default a pool returns everything to the driver
+// at every synchronisation, which would re-map the staging memory on each call.  The process's default pool is left alone
+// (other cudaMallocAsync users of the host application keep the behaviour they configured).
+static cudaMemPool_t g_pool[64] = {};
+static std::mutex g_pool_mu;
+static cudaMemPool_t device_pool(int device)
+{
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (!g_pool[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            g_pool[device] = pool;
+        } else cudaGetLastError();
+    }
+    return g_pool[device];
+}
+// cudaMallocAsync from the private pool (falls back to the default pool if it could not be created)
+static cudaError_t pool_alloc(void **p, size_t bytes, int device, cudaStream_t s)
+{
+    cudaMemPool_t pool = device_pool(device);
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, s) : cudaMallocAsync(p, bytes, s);
+}
+// gives the pool's cached memory back to the driver (zj_release_device_caches)
+extern "C" void zj_capi_trim_pools(void)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (int d = 0; d < 64; d++) if (g_pool[d]) cudaMemPoolTrimTo(g_pool[d], 0);
+    cudaGetLastError();
+}
+
 static int set_device(int device)
 {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return ZJ_ERR_NO_DEVICE; }
     if (device < 0 || device >= n) return ZJ_ERR_NO_DEVICE;
     CU(cudaSetDevice(device));
-    // keep the stream-ordered pool's memory across calls: by default it is returned to the driver at every
-    // synchronisation, which makes each zj_gpu_reconstruct re-map gigabytes of staging memory
-    static std::mutex mu;
-    static bool tuned[64] = {false};
-    std::lock_guard<std::mutex> lock(mu);
-    if (device < 64 && !tuned[device]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-        tuned[device] = true;
-    }
     return ZJ_OK;
 }
 
@@ -334,7 +359,7 @@ static int batch_create_impl(int device, const zj_image *imgs, size_t n, uint8_t
         k = e;
     }
     if (!host.empty()) {
-        cudaError_t e = pooled ? cudaMallocAsync((void **)&b->d_images, host.size() * sizeof(DevImage), ps)
+        cudaError_t e = pooled ? pool_alloc((void **)&b->d_images, host.size() * sizeof(DevImage), device, ps)
                                : cudaMalloc(&b->d_images, host.size() * sizeof(DevImage));
         if (e != cudaSuccess) { delete b; return cuda_fail(e, "cudaMalloc(descriptors)"); }
         // (pageable source: the async copy returns once the data sits in the driver's staging buffer)
@@ -447,7 +472,7 @@ int zj_gpu_convert_device(int device, void *stream, const uint8_t *src_dev, uint
     ci.src = src_dev; ci.dst = dst_dev; ci.width = width; ci.height = height; ci.nc = nc;
     cudaStream_t s = (cudaStream_t)stream;
     ConvImage *d_ci = nullptr;
-    CU(cudaMallocAsync((void **)&d_ci, sizeof(ci), s));
+    CU(pool_alloc((void **)&d_ci, sizeof(ci), device, s));
     cudaError_t e = cudaMemcpyAsync(d_ci, &ci, sizeof(ci), cudaMemcpyHostToDevice, s);   // (pageable source: staged before the call returns)
     if (e == cudaSuccess) { e = launch_convert(d_ci, 1, nc, ci.ow, ci.oh, *d, s); g_launches.fetch_add(1); }
     cudaFreeAsync(d_ci, s);
@@ -506,8 +531,8 @@ int zj_gpu_reconstruct_device_ex(int device, void *stream, const zj_image *imgs,
     if (n == 0) return ZJ_OK;
     uint8_t *scratch = nullptr;
     ConvImage *d_conv = nullptr;
-    CU(cudaMallocAsync((void **)&scratch, scratch_bytes, s));
-    cudaError_t e = cudaMallocAsync((void **)&d_conv, n * sizeof(ConvImage), s);
+    CU(pool_alloc((void **)&scratch, scratch_bytes, device, s));
+    cudaError_t e = pool_alloc((void **)&d_conv, n * sizeof(ConvImage), device, s);
     if (e != cudaSuccess) { cudaFreeAsync(scratch, s); return cuda_fail(e, "cudaMallocAsync(consumer descriptors)"); }
     for (size_t i = 0; i < n; i++) conv[i].src = scratch + u8_off[i];
     e = cudaMemcpyAsync(d_conv, conv.data(), n * sizeof(ConvImage), cudaMemcpyHostToDevice, s);

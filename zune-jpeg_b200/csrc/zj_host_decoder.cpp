@@ -1823,6 +1823,7 @@ static size_t slot_retain_bytes()
     return v;
 }
 extern "C" void zj_capi_release_stream_caches(void);   // zj_capi.cu (hidden)
+extern "C" void zj_capi_trim_pools(void);
 
 ZJ_API void zj_release_device_caches(void)
 {
@@ -1834,6 +1835,7 @@ ZJ_API void zj_release_device_caches(void)
         cudaGetLastError();
     }
     zj_capi_release_stream_caches();
+    zj_capi_trim_pools();
 }
 
 // Batch front door with the entropy stage on the GPU as well (zj_entropy.cu) for the JPEGs that allow it: baseline scans
