@@ -316,8 +316,9 @@ ZJ_API int zj_decode_batch_multi(const zj_options *o, const int *devices, size_t
 ZJ_API void zj_release_host_caches(void);
 /* Device-side state kept between calls, and its release.  zj_gpu_reconstruct[_submit] keeps, per host thread that called it,
  * its staging streams and up to three device staging buffers (256 MB sub-batches by default); zj_decode_batch_gpu[_device]
- * keeps two slots of device staging memory (>= 1 GB each once used; a slot that a call grew beyond ZJ_RETAIN_MB megabytes,
- * default 1024, is freed when that call ends), their streams and small pinned blocks.  zj_release_device_caches frees all of
+ * keeps two slots of device staging memory (>= 1 GB each once used, up to the 4 / 8 GB sub-batch budget; a slot that a call
+ * grew beyond ZJ_RETAIN_MB megabytes is freed when that call ends -- default 16384, i.e. never: re-allocating a 6.7 GB slot
+ * was measured at up to 119 ms per call), their streams and small pinned blocks.  zj_release_device_caches frees all of
  * it except what a thread is using at that moment (it waits for a zj_decode_batch_gpu call in flight); the next call
  * allocates again.  Call it when the process wants its HBM back, e.g. a data loader that shares the GPU with a training job. */
 ZJ_API void zj_release_device_caches(void);

@@ -1794,7 +1794,7 @@ ZJ_API int zj_decode_batch_multi(const zj_options *o, const int *devices, size_t
 
 // ---- state zj_decode_batch_gpu[_device] keeps between calls: two slots of device staging memory (at least 1 GB each once
 // used, grown to the sub-batch budget), their streams and pinned descriptor / status blocks.  zj_release_device_caches frees
-// them; a buffer larger than ZJ_RETAIN_MB (default 1024) is freed when the call that grew it ends.
+// them; a buffer larger than ZJ_RETAIN_MB (default 16384: never, in practice) is freed when the call that grew it ends.
 struct GpuSlot {
     cudaStream_t s = nullptr; uint8_t *mem = nullptr; size_t cap = 0;
     zj_batch *batch = nullptr;
@@ -1805,8 +1805,25 @@ struct GpuSlot {
     uint8_t *meta_host = nullptr, *st_host = nullptr;   // pinned: descriptors + tables + interval starts up, statuses down
     size_t meta_cap = 0, st_cap = 0;
     bool staged = false;
+    // the files of a sub-batch go up in chunks on auxiliary streams, each followed by the entropy kernel of its images: the
+    // kernel is latency-bound (one thread per restart interval, ~10 ms whatever the count), so the kernels of the chunks run
+    // side by side on the GPU and under the uploads of the later chunks
+    static constexpr int NAUX = 4;
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_meta = nullptr, ev_chunk[NAUX] = {};
+    bool aux_ready()
+    {
+        for (int k = 0; k < NAUX; k++) {
+            if (!aux[k] && cudaStreamCreateWithFlags(&aux[k], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (!ev_chunk[k] && cudaEventCreateWithFlags(&ev_chunk[k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+        if (!ev_meta && cudaEventCreateWithFlags(&ev_meta, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        return true;
+    }
     void release()      // streams, device staging memory and the pinned descriptor / status blocks
     {
+        for (int k = 0; k < NAUX; k++) { if (aux[k]) cudaStreamDestroy(aux[k]); if (ev_chunk[k]) cudaEventDestroy(ev_chunk[k]); }
+        if (ev_meta) cudaEventDestroy(ev_meta);
         if (mem) cudaFree(mem);
         if (s) cudaStreamDestroy(s);
         if (meta_host) cudaFreeHost(meta_host);
@@ -1819,7 +1836,9 @@ static std::mutex g_slot_mu;
 static GpuSlotCache g_slot_cache;
 static size_t slot_retain_bytes()
 {
-    static const size_t v = [] { const char *e = getenv("ZJ_RETAIN_MB"); long mb = e ? atol(e) : 1024; return (size_t)(mb < 0 ? 0 : mb) << 20; }();
+    // (default 16 GB: above any sub-batch budget, i.e. the slots are kept until zj_release_device_caches.  Re-allocating a
+    // 6.7 GB slot was measured at up to 119 ms per call -- four times the call itself)
+    static const size_t v = [] { const char *e = getenv("ZJ_RETAIN_MB"); long mb = e ? atol(e) : 16384; return (size_t)(mb < 0 ? 0 : mb) << 20; }();
     return v;
 }
 extern "C" void zj_capi_release_stream_caches(void);   // zj_capi.cu (hidden)
@@ -2047,7 +2066,6 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
             zj::EntImage &e = sl.eimg[t];
             const zj_decoder::BaselineGeom &g = it.pp.g;
             uint8_t *d_data = carve(lens[i] + 8);
-            ok = ok && cudaMemcpyAsync(d_data, bufs[i], lens[i], cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
             it.d->gpu_entropy_tables(reinterpret_cast<zj::EntTable *>(sl.meta_host + off_tab) + 6 * t);
             memcpy(sl.meta_host + off_seg + seg_at * 4, it.pp.seg_start.data(), (it.pp.n_seg + 1) * 4);
             sl.pix[t] = dev_out ? out[i] : carve(it.need);
@@ -2071,9 +2089,23 @@ static int decode_batch_gpu_impl(const zj_options *o, const uint8_t *const *bufs
         }
         if (ok) memcpy(sl.meta_host, sl.eimg.data(), take.size() * sizeof(zj::EntImage));
         ok = ok && off <= sl.cap && cudaMemcpyAsync(d_meta, sl.meta_host, meta_bytes, cudaMemcpyHostToDevice, sl.s) == cudaSuccess;
-        lap("upload files + tables", sl.s);
-        ok = ok && zj::launch_entropy(reinterpret_cast<const zj::EntImage *>(d_meta), (uint32_t)take.size(), max_seg, sl.s) == 0;
-        lap("entropy kernel", sl.s);
+        // files + entropy kernels, chunk by chunk on the auxiliary streams (behind the cleared planes and the descriptors)
+        static const size_t n_chunks_env = [] { const char *e = getenv("ZJ_GPU_ENTROPY_CHUNKS"); long v = e ? atol(e) : GpuSlot::NAUX; return (size_t)std::max(1L, std::min(v, (long)GpuSlot::NAUX)); }();
+        const size_t n_chunks = (take.size() >= 2 * n_chunks_env && sl.aux_ready()) ? n_chunks_env : 1;
+        ok = ok && (n_chunks == 1 || cudaEventRecord(sl.ev_meta, sl.s) == cudaSuccess);
+        for (size_t c = 0; c < n_chunks && ok; c++) {
+            const size_t t0 = take.size() * c / n_chunks, t1 = take.size() * (c + 1) / n_chunks;
+            cudaStream_t cs = n_chunks == 1 ? sl.s : sl.aux[c];
+            if (n_chunks > 1) ok = ok && cudaStreamWaitEvent(cs, sl.ev_meta, 0) == cudaSuccess;
+            uint32_t chunk_seg = 0;
+            for (size_t t = t0; t < t1 && ok; t++) {
+                ok = cudaMemcpyAsync(const_cast<uint8_t *>(sl.eimg[t].data), bufs[take[t]], lens[take[t]], cudaMemcpyHostToDevice, cs) == cudaSuccess;
+                chunk_seg = std::max(chunk_seg, sl.eimg[t].n_seg);
+            }
+            ok = ok && zj::launch_entropy(reinterpret_cast<const zj::EntImage *>(d_meta) + t0, (uint32_t)(t1 - t0), chunk_seg, cs) == 0;
+            if (n_chunks > 1) ok = ok && cudaEventRecord(sl.ev_chunk[c], cs) == cudaSuccess && cudaStreamWaitEvent(sl.s, sl.ev_chunk[c], 0) == cudaSuccess;
+        }
+        lap("files + entropy kernels", sl.s);
         ok = ok && cudaMemcpyAsync(sl.st_host, d_status, st_total, cudaMemcpyDeviceToHost, sl.s) == cudaSuccess;
         if (!ok) cudaGetLastError();
         sl.staged = ok;   // (not staged: nothing is published, these images go through the host path)
