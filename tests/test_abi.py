@@ -103,3 +103,51 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "zj_oracle" not in txt and "libzj_oracle" not in txt and "import oracle" not in txt, f
+
+
+@pytest.mark.gpu
+def test_release_caches_while_calls_are_in_flight():
+    """zj_release_device_caches / zj_release_host_caches may be called at any time: here from a thread of its own while four
+    threads run the batch front doors (host route, GPU-entropy route, device outputs).  Results stay correct, nothing crashes,
+    and after a final release the next call simply allocates again."""
+    import threading
+
+    import numpy as np
+
+    import jpeg_util
+    from zune_jpeg_b200 import _ffi, gpu
+    from zune_jpeg_b200.decoder import ColorSpace, ZuneJpegOptions, decode_batch
+    lib = _ffi.load()
+    opts = ZuneJpegOptions().set_out_colorspace(ColorSpace.RGB)
+    datas = [jpeg_util.synth_jpeg(20 + i, 640 + 32 * i, 360 + 16 * i, ("420", "444", "422")[i % 3], 90, restart_rows=i % 2) for i in range(6)]
+    want = decode_batch(datas, opts, threads=2)
+    assert all(isinstance(w, bytes) for w in want)
+    stop = threading.Event()
+    errors = []
+
+    def releaser():
+        while not stop.is_set():
+            lib.zj_release_device_caches()
+            lib.zj_release_host_caches()
+
+    def worker(k):
+        try:
+            for it in range(6):
+                got = decode_batch(datas, opts, threads=2, gpu_entropy=bool((k + it) & 1))
+                if got != want:
+                    errors.append((k, it, "pixels differ"))
+        except Exception as e:      # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    r = threading.Thread(target=releaser)
+    ws = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    r.start()
+    for w in ws:
+        w.start()
+    for w in ws:
+        w.join()
+    stop.set()
+    r.join()
+    assert not errors, errors[:3]
+    lib.zj_release_device_caches()
+    assert decode_batch(datas, opts, threads=2, gpu_entropy=True) == want
