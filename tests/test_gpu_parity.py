@@ -456,6 +456,18 @@ def test_gpu_entropy_decode_device_outputs():
     assert all(isinstance(r, DecodeErrors) for r in res)
 
 
+def test_gpu_entropy_decode_in_chunks():
+    """ZJ_GPU_ENTROPY_CHUNKS=4 (files, entropy kernels and reconstruction chunk by chunk on auxiliary streams; the setting is read
+    once per process, hence the child process): same pixels, same statuses."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("ZJ_GPU_ENTROPY_CHUNKS") != "4":
+        env = dict(os.environ, ZJ_GPU_ENTROPY_CHUNKS="4")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k", "test_gpu_entropy_decode"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_gpu_entropy_decode_fuzz():
     """Damaged restart-marker streams, many at once: whatever route an image ends up on (GPU intervals accepted, or the host
     stage after a rejected interval), pixels and per-image errors equal those of the host stage alone."""
