@@ -480,6 +480,47 @@ int zj_gpu_convert_device(int device, void *stream, const uint8_t *src_dev, uint
     return ZJ_OK;
 }
 
+// Hidden helpers for zj_decode_batch_gpu_device_ex (zj_host_decoder.cpp): scratch from this library's stream-ordered pool, and
+// the consumer over many images in as few launches as their pixel formats allow.
+extern "C" int zj_capi_pool_alloc(void **p, size_t bytes, int device, void *stream)
+{
+    int rc = set_device(device);
+    if (rc) return rc;
+    CU(pool_alloc(p, bytes, device, (cudaStream_t)stream));
+    return ZJ_OK;
+}
+extern "C" void zj_capi_pool_free(void *p, void *stream) { if (p) cudaFreeAsync(p, (cudaStream_t)stream); }
+extern "C" int zj_capi_convert_many(int device, void *stream, const uint8_t *const *src, const uint32_t *w, const uint32_t *h, const uint32_t *nc,
+                                    void *const *dst, size_t n, const zj_output_desc *d)
+{
+    int rc = desc_check(d);
+    if (rc) return rc;
+    rc = set_device(device);
+    if (rc) return rc;
+    if (n == 0) return ZJ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<ConvImage> conv(n);
+    for (size_t i = 0; i < n; i++) {
+        ConvImage &ci = conv[i];
+        ci.src = src[i]; ci.dst = dst[i]; ci.width = w[i]; ci.height = h[i]; ci.nc = nc[i];
+        rc = conv_shape(w[i], h[i], nc[i], d, &ci.ow, &ci.oh, &ci.oc);
+        if (rc) return rc;
+    }
+    ConvImage *d_conv = nullptr;
+    CU(pool_alloc((void **)&d_conv, n * sizeof(ConvImage), device, s));
+    cudaError_t e = cudaMemcpyAsync(d_conv, conv.data(), n * sizeof(ConvImage), cudaMemcpyHostToDevice, s);   // (pageable: staged before the call returns)
+    for (size_t k = 0; k < n && e == cudaSuccess;) {
+        size_t k1 = k;
+        uint32_t mw = 0, mh = 0;
+        while (k1 < n && conv[k1].nc == conv[k].nc && k1 - k < 65535) { mw = std::max(mw, conv[k1].ow); mh = std::max(mh, conv[k1].oh); k1++; }
+        if (mw && mh) { e = launch_convert(d_conv + k, (uint32_t)(k1 - k), conv[k].nc, mw, mh, *d, s); g_launches.fetch_add(1); }
+        k = k1;
+    }
+    cudaFreeAsync(d_conv, s);
+    if (e != cudaSuccess) return cuda_fail(e, "consumer launch");
+    return ZJ_OK;
+}
+
 // Sub-batch budget of the u8 intermediate (scratch memory of the call).  Measured on 128 4K images (profiles/README.md):
 // sub-batches small enough to stay in the 126 MB L2 between the two kernels (48 MB: 245 GP/s) lose more to under-filled
 // launches than the cache saves; 320 MB: 292 GP/s, the whole batch at once: 320 GP/s.  1 GB keeps the launches large and the

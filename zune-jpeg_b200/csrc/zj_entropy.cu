@@ -18,6 +18,7 @@
 // thousands of intervals in flight at once -- a batch of 64 8192x8192 images is 32768 independent intervals -- and no
 // PCIe upload of coefficient planes (201 MB per such image; its JPEG file is 12 MB).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "zj_entropy.h"
@@ -172,12 +173,14 @@ __device__ __forceinline__ void decode_block(Reader &r, const EntTable &dc, cons
     }
 }
 
+template <int ENT_LANES>
 __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(const EntImage *__restrict__ images)
 {
     __shared__ EntTable sT[6];
     __shared__ uint8_t sZ[80];   // (threads index it with different positions: a constant-bank access would be serialised)
     const EntImage &im = images[blockIdx.y];
-    if (blockIdx.x * ENT_THREADS >= im.n_seg) return;
+    constexpr u32 ENT_SEGS = ENT_THREADS / 32 * ENT_LANES;   // intervals per CTA
+    if (blockIdx.x * ENT_SEGS >= im.n_seg) return;
     {   // the image's tables: [dc, ac] per component
         const u32 words = (u32)(sizeof(EntTable) / 4) * 2u * im.ncomp;
         const u32 *src = reinterpret_cast<const u32 *>(im.tables);
@@ -186,7 +189,8 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(const EntImage *__
     }
     for (u32 i = threadIdx.x; i < 80; i += ENT_THREADS) sZ[i] = c_unzigzag[i];
     __syncthreads();
-    const u32 k = blockIdx.x * ENT_THREADS + threadIdx.x;
+    if ((threadIdx.x & 31u) >= (u32)ENT_LANES) return;
+    const u32 k = blockIdx.x * ENT_SEGS + (threadIdx.x >> 5) * ENT_LANES + (threadIdx.x & 31u);
     if (k >= im.n_seg) return;
 
     Reader r;
@@ -248,12 +252,25 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(const EntImage *__
     im.status[k] = ok ? 0 : 1;
 }
 
+template <int LANES>
+static int launch_lanes(const EntImage *d_images, uint32_t n_images, uint32_t max_seg, cudaStream_t s)
+{
+    constexpr uint32_t SEGS = ENT_THREADS / 32 * LANES;
+    dim3 grid((max_seg + SEGS - 1) / SEGS, n_images);
+    entropy_kernel<LANES><<<grid, ENT_THREADS, 0, s>>>(d_images);
+    return (int)cudaGetLastError();
+}
+
 int launch_entropy(const EntImage *d_images, uint32_t n_images, uint32_t max_seg, void *stream)
 {
     if (n_images == 0 || max_seg == 0) return 0;
-    dim3 grid((max_seg + ENT_THREADS - 1) / ENT_THREADS, n_images);
-    entropy_kernel<<<grid, ENT_THREADS, 0, (cudaStream_t)stream>>>(d_images);
-    return (int)cudaGetLastError();
+    static const int forced = [] { const char *e = getenv("ZJ_ENTROPY_LANES"); return e ? atoi(e) : 0; }();
+    const uint64_t intervals = (uint64_t)n_images * max_seg;          // (an upper bound: images of one launch may differ)
+    const int lanes = forced ? forced : (intervals < 12000 ? 8 : (intervals < 24000 ? 16 : 32));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (lanes <= 8) return launch_lanes<8>(d_images, n_images, max_seg, s);
+    if (lanes <= 16) return launch_lanes<16>(d_images, n_images, max_seg, s);
+    return launch_lanes<32>(d_images, n_images, max_seg, s);
 }
 
 }  // namespace zj

@@ -1843,6 +1843,10 @@ static size_t slot_retain_bytes()
 }
 extern "C" void zj_capi_release_stream_caches(void);   // zj_capi.cu (hidden)
 extern "C" void zj_capi_trim_pools(void);
+extern "C" int zj_capi_pool_alloc(void **p, size_t bytes, int device, void *stream);
+extern "C" void zj_capi_pool_free(void *p, void *stream);
+extern "C" int zj_capi_convert_many(int device, void *stream, const uint8_t *const *src, const uint32_t *w, const uint32_t *h, const uint32_t *nc,
+                                    void *const *dst, size_t n, const zj_output_desc *d);
 
 ZJ_API void zj_release_device_caches(void)
 {
@@ -2256,7 +2260,7 @@ ZJ_API int zj_decode_batch_gpu_device_ex(const zj_options *o, const uint8_t *con
         if (dd) zj_decoder_free(dd);
     }
     uint8_t *scratch = nullptr;
-    if (total && cudaMalloc(&scratch, total) != cudaSuccess) { cudaGetLastError(); return ZJ_ERR_OOM; }
+    if (total) { const int arc = zj_capi_pool_alloc((void **)&scratch, total, opt.device, nullptr); if (arc != ZJ_OK) return arc; }
     std::vector<uint8_t *> mid(n);
     std::vector<size_t> mid_len(n);
     // (images whose headers do not parse get a dummy one-byte slot: the decode call reports their error)
@@ -2264,19 +2268,25 @@ ZJ_API int zj_decode_batch_gpu_device_ex(const zj_options *o, const uint8_t *con
     int rc = zj_decode_batch_gpu_device(&opt, bufs, lens, n, mid.data(), mid_len.data(), status, n_gpu_entropy);
     int failed = rc;
     if (rc >= 0) {
+        // every decoded image through the consumer: one launch per run of equal pixel formats
+        std::vector<const uint8_t *> csrc;
+        std::vector<void *> cdst;
+        std::vector<uint32_t> cw, ch, cnc;
+        const size_t es = d->dtype == ZJ_DTYPE_U8 ? 1 : (d->dtype == ZJ_DTYPE_F16 ? 2 : 4);
         for (size_t i = 0; i < n; i++) {
             if (status[i] != ZJ_OK) { out_len[i] = 0; continue; }
             const Geo &g = geo[i];
-            const size_t have = out_len[i];
-            const size_t es = d->dtype == ZJ_DTYPE_U8 ? 1 : (d->dtype == ZJ_DTYPE_F16 ? 2 : 4);
             const size_t need = (size_t)(g.w >> d->scale_log2) * (g.h >> d->scale_log2) * ((d->channels == 3 && g.nc == 4) ? 3 : g.nc) * es;
-            int st = zj_gpu_convert_device(opt.device, nullptr, mid[i], g.w, g.h, g.nc, d, out_dev[i], have);
-            if (st != ZJ_OK) { status[i] = st; failed++; out_len[i] = 0; }
-            else out_len[i] = need;
+            if (!out_dev[i]) { status[i] = ZJ_ERR_INVALID_ARG; failed++; out_len[i] = 0; continue; }
+            if (out_len[i] < need) { status[i] = ZJ_ERR_SHORT_OUTPUT; failed++; out_len[i] = 0; continue; }
+            out_len[i] = need;
+            csrc.push_back(mid[i]); cdst.push_back(out_dev[i]); cw.push_back(g.w); ch.push_back(g.h); cnc.push_back(g.nc);
         }
-        if (cudaStreamSynchronize(nullptr) != cudaSuccess) { cudaGetLastError(); failed = ZJ_ERR_CUDA; }
+        int crc = zj_capi_convert_many(opt.device, nullptr, csrc.data(), cw.data(), ch.data(), cnc.data(), cdst.data(), csrc.size(), d);
+        if (crc == ZJ_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) { cudaGetLastError(); crc = ZJ_ERR_CUDA; }
+        if (crc != ZJ_OK) failed = crc;
     }
-    if (scratch) cudaFree(scratch);
+    zj_capi_pool_free(scratch, nullptr);
     return failed;
 }
 
