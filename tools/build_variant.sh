@@ -9,7 +9,7 @@ out=$root/build/variants
 mkdir -p $out/obj_$name
 for f in zj_kernels.cu zj_capi.cu zj_entropy.cu zj_consumer.cu zj_host_decoder.cpp; do
   o=$out/obj_$name/${f%.*}.o
-  if [ $f = zj_kernels.cu ] || [ ! -f $o ] || [ $src/$f -nt $o ]; then
+  if [ $f = zj_kernels.cu ] || [ $f = zj_entropy.cu ] || [ ! -f $o ] || [ $src/$f -nt $o ]; then
     rm -f $o
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-O3 "$@" -x cu -c $src/$f -o $o &
   fi
