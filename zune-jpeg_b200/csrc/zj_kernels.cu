@@ -25,9 +25,6 @@
 #ifndef ZF_T2PAIR
 #define ZF_T2PAIR 1
 #endif
-#ifndef ZF_LO6
-#define ZF_LO6 0
-#endif
 #if ZF_HINTS
 #define ZF_LIKELY(x) __builtin_expect(!!(x), 1)
 #define ZF_UNLIKELY(x) __builtin_expect(!!(x), 0)
@@ -46,6 +43,12 @@
 #endif
 #ifndef ZF_EMIT_LOOP
 #define ZF_EMIT_LOOP 0
+#endif
+#ifndef ZF_ROTATE_HV
+#define ZF_ROTATE_HV 0       // 4:2:0: the pass-1 producer jobs (Cb, Cr, halo) rotate over the four producer warps with the strip
+#endif
+#ifndef ZF_DEFER_EMPTY
+#define ZF_DEFER_EMPTY 1     // (rotated form) wait for the plane buffer between the row pass and the column pass
 #endif
 
 // The per-sample generic path (slow_pixel) used to be kept out of line.  With that call inside a consumer warp,
@@ -66,9 +69,32 @@ typedef uint32_t u32;
 // ------------------------------------------------------------------------------------------------ IDCT
 // 1-D 8-point kernel: reference src/idct/scalar.rs:79-166 == src/idct/avx2.rs:251-331.  All arithmetic is
 // in Z/2^32 (u32), the final shift is arithmetic.
+// ZF_IDCT_MAD: the butterfly written as the 43 operations it needs (27 multiply-adds / adds of the even and odd parts + 16 for
+// the final sums and shifts) with the multiply-adds pinned as `mad.lo` -- the plain expression form below compiled to 50 (the
+// rounding bias as four separate adds, the products of p3 / p4 formed once and added twice).  Regrouping is exact: all of it is
+// arithmetic in Z/2^32.
+#ifndef ZF_IDCT_MAD
+#define ZF_IDCT_MAD 1
+#endif
+template <int K> __device__ __forceinline__ u32 madk(u32 a, u32 c) { u32 d; asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(K), "r"(c)); return d; }
+
 template <int SH>
 __device__ __forceinline__ void idct8(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s4, u32 &s5, u32 &s6, u32 &s7, const u32 bias)
 {
+#if ZF_IDCT_MAD
+    const u32 p1 = (s2 + s6) * 2217u;
+    const u32 t2 = madk<-7567>(s6, p1), t3 = madk<3135>(s2, p1);
+    const u32 v = (s0 << 12) + bias;
+    const u32 t0 = madk<4096>(s4, v), t1 = madk<-4096>(s4, v);
+    const u32 x0 = t0 + t3, x3 = t0 - t3, x1 = t1 + t2, x2 = t1 - t2;
+    const u32 p3 = s7 + s3, p4 = s5 + s1, q1 = s7 + s1, q2 = s5 + s3;
+    const u32 p5 = (p3 + p4) * 4816u;
+    const u32 r1 = madk<-3685>(q1, p5), r2 = madk<-10497>(q2, p5);
+    const u32 a = madk<1223>(s7, madk<-8034>(p3, r1));
+    const u32 c = madk<12586>(s3, madk<-8034>(p3, r2));
+    const u32 b = madk<8410>(s5, madk<-1597>(p4, r2));
+    const u32 d = madk<6149>(s1, madk<-1597>(p4, r1));
+#else
     u32 p1 = (s2 + s6) * 2217u;
     u32 t2 = p1 + s6 * (u32)(-7567);
     u32 t3 = p1 + s2 * 3135u;
@@ -84,6 +110,7 @@ __device__ __forceinline__ void idct8(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s
     p3 *= (u32)(-8034);
     p4 *= (u32)(-1597);
     d += q1 + p4; c += q2 + p3; b += q2 + p4; a += q1 + p3;
+#endif
     s0 = (u32)((int)(x0 + d) >> SH);
     s1 = (u32)((int)(x1 + c) >> SH);
     s2 = (u32)((int)(x2 + b) >> SH);
@@ -100,6 +127,16 @@ __device__ __forceinline__ void idct8(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s
 template <int SH>
 __device__ __forceinline__ void idct8_lo4(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s4, u32 &s5, u32 &s6, u32 &s7, const u32 bias)
 {
+#if ZF_IDCT_MAD
+    // 29 operations: every intermediate is a two-term combination of (s0, s2) or (s1, s3) with the constants summed up front
+    const u32 t0 = (s0 << 12) + bias;
+    const u32 x0 = madk<2217 + 3135>(s2, t0), x3 = madk<-(2217 + 3135)>(s2, t0), x1 = madk<2217>(s2, t0), x2 = madk<-2217>(s2, t0);
+    const u32 c48 = s3 * 4816u, d48 = s1 * 4816u;
+    const u32 dd = madk<6149 - 3685 + 4816 - 1597>(s1, c48);            // d * 6149 + q1 + p4
+    const u32 cc = madk<12586 - 10497 + 4816 - 8034>(s3, d48);          // c * 12586 + q2 + p3
+    const u32 bb = madk<4816 - 10497>(s3, s1 * (u32)(4816 - 1597));     // q2 + p4
+    const u32 aa = madk<4816 - 3685>(s1, s3 * (u32)(4816 - 8034));      // q1 + p3
+#else
     const u32 t2 = s2 * 2217u;                 // p1 + s6 * -7567 with s6 = 0
     const u32 t3 = s2 * (2217u + 3135u);       // p1 + s2 * 3135
     const u32 t0 = (s0 << 12) + bias;          // t0 == t1 when s4 = 0
@@ -111,6 +148,7 @@ __device__ __forceinline__ void idct8_lo4(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u3
     const u32 p3 = c * (u32)(-8034);           // p3 = a + c = c
     const u32 p4 = d * (u32)(-1597);           // p4 = b + d = d
     const u32 dd = d * 6149u + q1 + p4, cc = c * 12586u + q2 + p3, bb = q2 + p4, aa = q1 + p3;
+#endif
     s0 = (u32)((int)(x0 + dd) >> SH);
     s1 = (u32)((int)(x1 + cc) >> SH);
     s2 = (u32)((int)(x2 + bb) >> SH);
@@ -361,6 +399,20 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
     }
 }
 
+// ---- halo blocks: ONE sample column instead of the whole block.  The consumers' packed path reads exactly one column of a
+// chroma halo block -- the last one of the left neighbour, the first one of the right neighbour (and of the "stale neighbour"
+// block of tile 0) -- so for a job that holds nothing but halo blocks the row pass only produces that column:
+//   out[r][0] = (E + O + 512) >> 10,  out[r][7] = (E - O + 512) >> 10   with, from the butterfly of idct8 (all in Z/2^32, so the
+//   regrouping is exact):  E = 4096 (s0 + s4) + 5352 s2 + 2217 s6,   O = 5683 s1 + 4816 s3 + 3219 s5 + 1131 s7
+// and leaves it in the scratch where the ORDINARY column pass of column group 0 finds it (position 0 for a first column, position 3
+// for a last column, whose four output bytes then land on block columns 4-7); the other three columns of that group are computed
+// from stale scratch and land in halo samples nobody reads.  About 400 instead of 940 warp-instructions for the halo job of a
+// strip-tile (12 blocks in 32 lanes: it was a seventh of the producers' instructions in 4:2:0) for 60 lines of new hot code --
+// a separate single-column column pass was measured too: 345 SASS lines more, and the 4:2:0 kernel LOST 5.5 % (instruction cache).
+// Only taken when no unit of the tile goes through the per-sample path and the raw row tail (Q4g) stays inside the tile.
+#ifndef ZF_HALO_COL
+#define ZF_HALO_COL 0
+#endif
 #ifndef ZF_UNROLL_HV
 #define ZF_UNROLL_HV 1
 #endif
@@ -378,9 +430,11 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
 #endif
 // UNROLL: 1 = the row-pair loop stays rolled (4:2:0 / 4:4:0: the consumers' hot code leaves no room in the 32 KB instruction
 // cache for more); 4 = unrolled (everything that depends on the row pair becomes static: +7 % on 4:2:2, +10 % luma-only)
-template <int UNROLL, typename AfterRows>
+// halo: 0 = an ordinary job; warp-uniform non-zero = a job of halo blocks reduced to one column each (1: this lane's block
+// needs its first column, 2: its last column)
+template <int UNROLL, bool HALO, typename AfterRows>
 __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, const u32 sc, const u32 *__restrict__ qtw, uint8_t *__restrict__ dst, const int dst_stride,
-                                            AfterRows after_rows)
+                                            const int halo, AfterRows after_rows)
 {
     constexpr u32 CH = 16u * ZF_PRODUCERS;
     // Row pairs are visited from the bottom (rows 6-7) to the top (rows 0-1): the first word of the LAST visited pair is then
@@ -388,6 +442,28 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
     // everything except that word's low half (all 63 AC coefficients); nz collects, one bit per pair, which pairs were
     // transformed (warp-uniform: bit 3 = rows 6-7 ... bit 0 = rows 0-1).
     u32 acc = 0, carry = 0, nz = 0;
+    // (the vote makes the condition warp-uniform FOR THE COMPILER: `halo` derives from the thread index, and a branch it takes
+    // for divergent wraps the ordinary loop below in convergence barriers and takes its counters out of the uniform registers --
+    // measured: 6 % of the whole kernel)
+    const bool halo_job = HALO && __any_sync(0xffffffffu, halo != 0);
+    if (halo_job) {
+        const u32 sg = halo == 2 ? 0xffffffffu : 1u;
+        const u32 k1 = 5683u * sg, k3 = 4816u * sg, k5 = 3219u * sg, k7 = 1131u * sg;
+        const u32 o = sc + (halo == 2 ? 12u : 0u);
+#pragma unroll 1
+        for (int r = 7; r >= 0; r--) {            // bottom-up, as below: `carry` is left with the word that holds the DC coefficient
+            u32 w0, w1, w2, w3;
+            lds128(sl ^ (u32)(r << 4), w0, w1, w2, w3);
+            acc |= carry | w1 | w2 | w3;
+            carry = w0;
+            const uint4 q = *reinterpret_cast<const uint4 *>(qtw + 4 * r);
+            const u32 s0 = dp2a_lo(w0, q.x), s1 = dp2a_hi(w0, q.x), s2 = dp2a_lo(w1, q.y), s3 = dp2a_hi(w1, q.y);
+            const u32 s4 = dp2a_lo(w2, q.z), s5 = dp2a_hi(w2, q.z), s6 = dp2a_lo(w3, q.w), s7 = dp2a_hi(w3, q.w);
+            const u32 v = 512u + ((s0 + s4) << 12) + s2 * 5352u + s6 * 2217u + s1 * k1 + s3 * k3 + s5 * k5 + s7 * k7;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(o + (u32)(2 * r) * CH), "r"((u32)((int)v >> 10)) : "memory");
+        }
+        nz = 0xfu;                                 // every row was produced: the 8-input column pass
+    } else
 #pragma unroll UNROLL
     for (int i = 96; i >= 0; i -= 32) {        // i = 32 * row pair: byte offset in the slot and in the table, 1/256 of the scratch offset
         u32 a0, a1, a2, a3, b0, b1, b2, b3;
@@ -449,8 +525,11 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
 #pragma unroll 1
         for (int g = 0; g < 2; g++) col_pass<4>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
     } else {
+        // (a halo job: column group 0 only, and a last column's four bytes go to block columns 4-7)
+        const int g1 = halo_job ? 1 : 2;
+        uint8_t *const d0 = (HALO && halo == 2) ? dst + 4 : dst;
 #pragma unroll 1
-        for (int g = 0; g < 2; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, dst + 4 * g, dst_stride);
+        for (int g = 0; g < g1; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, d0 + 4 * g, dst_stride);
     }
 }
 
@@ -741,13 +820,20 @@ __device__ __forceinline__ void convert_pair(u32 y, u32 cb, u32 cr, u32 &r, u32 
 #ifndef ZF_CONV_HI
 #define ZF_CONV_HI 2
 #endif
-__device__ __forceinline__ void convert_pair_hi(u32 y, u32 cb, u32 cr, u32 &r, u32 &g, u32 &b, const u32 k)
+#ifndef ZF_KR
+#define ZF_KR 1         // 1: the red channel's bias rides on a second lane constant (one 32-bit add fewer per lane pair, one register more)
+#endif
+__device__ __forceinline__ void convert_pair_hi(u32 y, u32 cb, u32 cr, u32 &r, u32 &g, u32 &b, const u32 k, const u32 kr)
 {
     const u32 y32 = y << 5;
 #if ZF_CONV_HI == 2
     // every channel is biased so that ONE lane constant (-16384, kept in a register by the caller) brings it back: the biases
     // ride on immediates of 32-bit adds (all lanes stay inside [0, 65535], so the lanes never carry into each other)
+#if ZF_KR
+    r = minrelu2(vadd2(cr * 45u + y32, kr), 0x1FFF1FFFu) * 8u;                                     // kr = -5760 on both lanes: 45cr + 32y never leaves [0, 21075]
+#else
     r = minrelu2(vadd2(cr * 45u + y32 + 0x29802980u, k), 0x1FFF1FFFu) * 8u;                        // +10624 = 16384 - 5760
+#endif
     g = minrelu2(vadd2(y32 + 0x511F511Fu - cb * 11u - cr * 23u, k), 0x1FFF1FFFu) * 8u;             // +20767 = 16384 + 4352 + 31
     b = minrelu2(vadd2(minu2(cb * 113u + y * 64u + 0x07800780u, 0x7FFF7FFFu), k), 0x3FFF3FFFu) * 4u;   // +1920 = 16384 - 14464
 #else
@@ -1162,6 +1248,25 @@ __device__ __forceinline__ void T2pair(u32 a, u32 b, u32 &n, u32 &f)
     f = ((b * 3u + a + 0x00020002u) >> 2) & 0x00ff00ffu;
 #endif
 }
+// ZF_VSCALE (4:2:0 packed path): the vertical blend hands 4 * T(a, b) (1) or 4 * T(a, b) + 2 (2) to the horizontal filter instead
+// of T(a, b): the `>> 2` of the blend becomes part of the filter's own shift --
+//   (3 * 4N + 4L + 8) >> 4  ==  (3N + L + 2) >> 2  ==  (3 * (4N + 2) + (4L + 2)) >> 4      (exact: everything is a multiple of 4)
+// which takes two shifts out of every T2pair (1) and the filter's separate add out of every output pair as well (2).
+// Lanes stay below 3 * 1538 + 1538 + 8 = 6160.
+#ifndef ZF_VSCALE
+#define ZF_VSCALE 1
+#endif
+__device__ __forceinline__ void T2pair_s(u32 a, u32 b, u32 &n, u32 &f, const u32 mask)
+{
+    const u32 s = a + b + 0x00020002u;
+#if ZF_VSCALE == 2
+    n = ((s + 2u * a) & mask) | 0x00020002u;
+    f = ((s + 2u * b) & mask) | 0x00020002u;
+#else
+    n = (s + 2u * a) & 0xFFFCFFFCu;
+    f = (s + 2u * b) & 0xFFFCFFFCu;
+#endif
+}
 __device__ __forceinline__ u32 evens(u32 w) { return prmt(w, 0u, 0x4240u); }  // bytes 0,2 -> 16-bit lanes
 __device__ __forceinline__ u32 odds(u32 w) { return prmt(w, 0u, 0x4341u); }   // bytes 1,3 -> 16-bit lanes
 
@@ -1192,11 +1297,33 @@ __device__ __forceinline__ void hfilter16(u32 h, const u32 r[4], u32 E[4], u32 O
     }
 }
 
+// the same filter on inputs scaled as ZF_VSCALE says (r[k], h = 4 * sample (+ 2)); results are the unscaled ones of hfilter16
+__device__ __forceinline__ void hfilter16_s(u32 h, const u32 r[4], u32 E[4], u32 O[4])
+{
+    u32 L[5];
+    L[0] = prmt(h, r[0], 0x5410u);
+    L[1] = prmt(r[0], r[1], 0x5432u);
+    L[2] = prmt(r[1], r[2], 0x5432u);
+    L[3] = prmt(r[2], r[3], 0x5432u);
+    L[4] = prmt(r[3], h, 0x7632u);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#if ZF_VSCALE == 2
+        E[k] = ((r[k] * 3u + L[k]) >> 4) & 0x01ff01ffu;
+        O[k] = ((r[k] * 3u + L[k + 1]) >> 4) & 0x01ff01ffu;
+#else
+        const u32 p3 = r[k] * 3u + 0x00080008u;
+        E[k] = ((p3 + L[k]) >> 4) & 0x01ff01ffu;
+        O[k] = ((p3 + L[k + 1]) >> 4) & 0x01ff01ffu;
+#endif
+    }
+}
+
 // 16 pixels of one row -> 48 interleaved bytes.  yw: the 16 luma bytes; cbE/cbO/crE/crO: chroma in the E/O
 // arrangement of hfilter16.  nw = number of leading 32-bit words to store (12, or fewer when the row's tail chunk
 // overwrites the rest, worker.rs:221-246); vec = 16-byte stores are aligned.
 __device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 cbE[4], const u32 cbO[4], const u32 crE[4], const u32 crO[4],
-                                       const bool ycc, const int nw, const bool vec, const u32 sel, const u32 kk)
+                                       const bool ycc, const int nw, const bool vec, const u32 sel, const u32 kk, const u32 kr = 0u)
 {
     // sel: byte selector of the first interleave step (the channel values sit in bytes 1 and 3 after convert_pair_hi, in bytes
     // 0 and 2 otherwise); kk: the lane constant of convert_pair_hi -- both held in registers by the caller
@@ -1209,8 +1336,8 @@ __device__ __forceinline__ void emit16(uint8_t *dst, const u32 yw[4], const u32 
             c0E = yE; c1E = cbE[k]; c2E = crE[k]; c0O = yO; c1O = cbO[k]; c2O = crO[k];
         } else {
 #if ZF_CONV_HI
-            convert_pair_hi(yE, cbE[k], crE[k], c0E, c1E, c2E, kk);
-            convert_pair_hi(yO, cbO[k], crO[k], c0O, c1O, c2O, kk);
+            convert_pair_hi(yE, cbE[k], crE[k], c0E, c1E, c2E, kk, kr);
+            convert_pair_hi(yO, cbO[k], crO[k], c0O, c1O, c2O, kk, kr);
 #else
             convert_pair(yE, cbE[k], crE[k], c0E, c1E, c2E);
             convert_pair(yO, cbO[k], crO[k], c0O, c1O, c2O);
@@ -1355,54 +1482,47 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                              : im.coeff[comp] + (((size_t)s_begin * FT::CBR + br) * mcu_x + gcol) * 64;
         };
         const u32 stepY = (u32)(FT::YBR * ybpr * 64), stepC = (u32)(FT::CBR * mcu_x * 64);   // i16 per strip
-        // this thread's own two blocks: where the samples go, which table
-        u32 pk[2];                       // bits 0-15 byte offset in the plane buffer, 16 active, 17 chroma, 18-19 table
-        // this warp's staging jobs
-        const int16_t *q0[2], *q1[2];    // lane pointers into run 0 / run 1 (mode 3: the lane's own block)
-        u32 jm[2];                       // bits 0-7 lim0, 8-15 lim1 (+64 bias), 16-17 mode: 0 none, 1 one run of 32, 2 two runs of 16, 3 lone blocks
-#pragma unroll
-        for (int ps = 0; ps < 2; ps++) {
+        // One staging job = the 32 consecutive list entries [B0, B0 + 32) of a warp: where this lane's block of the job goes (pk),
+        // how the warp copies the job's runs (g0 / g1 lane pointers at the CTA's first strip, jm).
+        //   pk: bits 0-15 byte offset in the plane buffer, 16 active, 17 chroma, 18-19 table, 20 left halo block
+        //   jm: bits 0-7 chunk k of the cooperative copy is inside the run, bit 8 the lane copies its own (lone) block
+        auto setup_job = [&](const int B0, u32 &pkj, const int16_t *&g0, const int16_t *&g1, u32 &jmj) {
             int comp, br, gcol, lcol;
-            // pass 0: job wq.  Pass 1: the jobs after the first four, handed out so that a warp whose pass-0 job is a (cheap)
-            // chroma job gets one first -- without sub-sampling warps 0,1 transform luma and 2,3 take Cb, then Cr; in 4:2:2 the
-            // lone halo job goes to a chroma warp.  (4:2:0 / 4:4:0: all four pass-0 jobs are luma, order is irrelevant.)
-            const int jw = ps == 0 ? wq : ((wq + ((MODE == MODE_NONE || MODE == MODE_H) ? 2 : 0)) & 3);
-            decode(jw * 32 + lane + ps * ZF_PRODUCERS, comp, br, gcol, lcol);
+            decode(B0 + lane, comp, br, gcol, lcol);
             const bool active = gcol >= 0;
-            pk[ps] = (comp == 0 ? (u32)(br * 8 * TWY + lcol) : (u32)(FT::YBYTES + (comp - 1) * FT::CBYTES + br * 8 * CS + lcol)) |
-                     (active ? 0x10000u : 0u) | (comp ? 0x20000u : 0u) | ((u32)comp << 18);
-            const int B0 = ps * ZF_PRODUCERS + jw * 32;          // first block of the warp
+            pkj = (comp == 0 ? (u32)(br * 8 * TWY + lcol) : (u32)(FT::YBYTES + (comp - 1) * FT::CBYTES + br * 8 * CS + lcol)) |
+                  (active ? 0x10000u : 0u) | (comp ? 0x20000u : 0u) | ((u32)comp << 18) |
+                  ((comp != 0 && lcol == 0) ? 0x100000u : 0u);   // bit 20: left halo block (its LAST column is the one the consumers read)
             const int lsub = lane >> 3, lch = lane & 7;
-            q0[ps] = q1[ps] = im.coeff[0];
-            int mode = 0, lim0 = 0, lim1 = 0;
+            g0 = g1 = im.coeff[0];
+            int mode = 0, lim0 = 0, lim1 = 0;   // mode: 0 none, 1 one run of 32, 2 two runs of 16, 3 lone blocks
             if (FT::DENSE) {
-                if (active) { mode = 3; q0[ps] = block_ptr(comp, br, gcol); }
+                if (active) { mode = 3; g0 = block_ptr(comp, br, gcol); }
             } else if (B0 < FT::NY + 2 * FT::NC) {
-                int c0, b0r, g0, l0;
-                decode(B0, c0, b0r, g0, l0);
+                int c0, b0r, gg0, l0;
+                decode(B0, c0, b0r, gg0, l0);
                 const bool isY = B0 < FT::NY;
                 const int bpr = isY ? FT::YB : FT::CB;           // blocks per tile block row
                 const int col0 = isY ? (B0 % FT::YB) : ((B0 - FT::NY) % FT::NC) % FT::CB;
                 const int have = (isY ? nyb : ncb) - col0;       // valid blocks from col0 on
                 const int first = (isY ? yb0 : cb0) + col0;
-                if (bpr >= 32) { mode = 1; lim0 = min(max(have, 0), 32) - lsub; q0[ps] = block_ptr(c0, b0r, first) + lsub * 64 + lch * 8; }
+                if (bpr >= 32) { mode = 1; lim0 = min(max(have, 0), 32) - lsub; g0 = block_ptr(c0, b0r, first) + lsub * 64 + lch * 8; }
                 else {
                     mode = 2; lim0 = lim1 = min(max(have, 0), 16) - lsub;
-                    q0[ps] = block_ptr(c0, b0r, first) + lsub * 64 + lch * 8;
-                    q1[ps] = block_ptr(c0, b0r + 1, first) + lsub * 64 + lch * 8;
+                    g0 = block_ptr(c0, b0r, first) + lsub * 64 + lch * 8;
+                    g1 = block_ptr(c0, b0r + 1, first) + lsub * 64 + lch * 8;
                 }
-            } else if (active) { mode = 3; q0[ps] = block_ptr(comp, br, gcol); }
-            // bit k: chunk k of the cooperative copy is inside the run; bit 8: the lane copies its own (lone) block
+            } else if (active) { mode = 3; g0 = block_ptr(comp, br, gcol); }
             u32 m = 0;
             for (int k = 0; k < 8; k++) {
                 const bool second = mode == 2 && k >= 4;
                 if ((mode == 1 || mode == 2) && 4 * (second ? k - 4 : k) < (second ? lim1 : lim0)) m |= 1u << k;
             }
             if (mode == 3) m = 0x100u;
-            if (mode == 2) q1[ps] -= 4 * 256;       // chunk k of run 1 is at q1 + (k - 4) * 256
-            else q1[ps] = q0[ps];
-            jm[ps] = m;
-        }
+            if (mode == 2) g1 -= 4 * 256;           // chunk k of run 1 is at g1 + (k - 4) * 256
+            else g1 = g0;
+            jmj = m;
+        };
         const u32 stage0 = (u32)__cvta_generic_to_shared(sDynAll) + (u32)(wq * 32) * 128u;     // the warp's slots of pass 0 (pass 1: + 16 KB)
         const u32 d_even = stage0 + (u32)(lane >> 3) * 128u + (u32)(((lane & 7) ^ (lane >> 3)) * 16);
         const u32 d_odd = stage0 + (u32)(lane >> 3) * 128u + (u32)(((lane & 7) ^ ((lane >> 3) + 4)) * 16);
@@ -1433,6 +1553,93 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+#if ZF_ROTATE_HV
+        if constexpr (MODE == MODE_HV) {
+            // 4:2:0 / the seven jobs of a strip-tile (4 luma, Cb, Cr, halo) over four warps: every warp transforms its own luma
+            // job in pass 0; the three pass-1 jobs ROTATE with the strip so that no warp is the heavy one all the time (statically
+            // assigned, two warps carried a chroma pass in every strip and set the pace of the whole CTA while the fourth idled
+            // at the `empty` barrier).  pair = which chroma plane a warp alternates on, half = on which strip parity:
+            //   strip parity == half: the warp's chroma job;  else, every other time ((it >> 1) & 1 == pair): the halo job.
+            //   it:      0        1        2        3
+            //   warp 0   Cb       halo     Cb       -          (pair 0, half 0)
+            //   warp 1   Cr       -        Cr       halo       (pair 1, half 0)
+            //   warp 2   halo     Cb       -        Cb         (pair 0, half 1)
+            //   warp 3   -        Cr       halo     Cr         (pair 1, half 1)
+            // Per four strips every warp does 4 luma + 2 chroma + 1 halo job.  The wait for the consumers to release the plane
+            // buffer sits between the row pass (which only writes the warp's scratch) and the column pass of pass 0.
+            // (through votes: wq derives from the thread index, and a branch on anything the compiler cannot prove warp-uniform
+            // wraps the transform loops in convergence barriers and takes their counters out of the uniform registers)
+            const int pair = __any_sync(0xffffffffu, (wq & 1) != 0) ? 1 : 0, half = __any_sync(0xffffffffu, (wq & 2) != 0) ? 1 : 0;
+            u32 pkL, pkC, pkH, jmL, jmC, jmH;
+            const int16_t *aL, *bL, *aC, *bC, *aH, *bH;
+            setup_job(wq * 32, pkL, aL, bL, jmL);
+            setup_job(FT::NY + pair * FT::NC, pkC, aC, bC, jmC);
+            setup_job(FT::NY + 2 * FT::NC, pkH, aH, bH, jmH);
+            aC += (u32)half * stepC; bC += (u32)half * stepC;                  // first strip of the warp's chroma job
+            aH += (u32)((1 - half) + 2 * pair) * stepC;                       // ... and of its halo job
+            const bool workL = __any_sync(0xffffffffu, (pkL & 0x10000u) != 0), workC = __any_sync(0xffffffffu, (pkC & 0x10000u) != 0),
+                       workH = __any_sync(0xffffffffu, (pkH & 0x10000u) != 0);
+            // the halo job may be reduced to the one column per block the consumers' packed path reads (idct_rolled): not when a unit
+            // of the tile goes through the per-sample path (it reads halo samples anywhere), nor when the raw row tail (Q4g) starts
+            // left of the tile (decided in front of the first pass 1, see below)
+            constexpr bool HALO_JOBS = ZF_HALO_COL && !FT::DENSE && ((FT::NY + 2 * FT::NC) % 32) == 0;
+            const bool tail_in_halo = cb0 + ncb == mcu_x && W - 36 - cb0 * 8 < 0;
+            bool halo_ok = HALO_JOBS;
+            issue(0, aL, bL, jmL);
+            aL += stepY; bL += stepY;
+            int buf = 0;
+            for (int it = 0; it < n_it; it++) {
+                ST *planes = sPlanes + buf * FT::BUF;
+                const bool hasC = (it & 1) == half, hasH = !hasC && ((it >> 1) & 1) == pair;
+#pragma unroll 1
+                for (int ps = 0; ps < 2; ps++) {
+                    const u32 pkk = ps ? (hasC ? pkC : pkH) : pkL;
+                    const bool work = ps ? (hasC ? workC : (hasH && workH)) : workL;
+                    const bool active = (pkk & 0x10000u) != 0;
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+#if !ZF_DEFER_EMPTY
+                    if (ps == 0 && it >= NB) bar_sync(BAR_EMPTY + buf);
+#endif
+                    // the copy issued from this pass: the warp's pass-1 job of this strip (if it has one), or its luma job of the next strip
+                    auto refill = [&]() {
+#if ZF_DEFER_EMPTY
+                        if (ps == 0 && it >= NB) bar_sync(BAR_EMPTY + buf);   // the consumers are done with this buffer
+#endif
+                        const int16_t *g0 = ps ? aL : (hasC ? aC : aH), *g1 = ps ? bL : (hasC ? bC : aH);
+                        const u32 m = ps ? (it + 1 < n_it ? jmL : 0u) : (hasC ? jmC : (hasH ? jmH : 0u));
+                        issue(ps, g0, g1, m);
+                        if (ps) { aL += stepY; bL += stepY; }
+                        else if (hasC) { aC += 2u * stepC; bC += 2u * stepC; }
+                        else if (hasH) aH += 4u * stepC;
+                    };
+                    if (HALO_JOBS && ps && it == 0) {
+                        // the consumers have counted their per-sample units long before the producers' first pass 1 (they arrived at
+                        // this barrier when their queue was complete): nobody waits here, it only orders the read of the count
+                        asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_QUEUE + 2), "n"(ZF_THREADS) : "memory");
+                        halo_ok = halo_ok && sSlowN == 0 && !tail_in_halo;
+                    }
+                    const int halo = (HALO_JOBS && ps && hasH && halo_ok) ? ((pkk & 0x100000u) ? 2 : 1) : 0;
+                    if (work) idct_rolled<FT::IDCT_UNROLL, HALO_JOBS>(active, active ? slx : zslot, scr, sQ[(pkk >> 18) & 3u], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, halo, refill);
+                    else refill();
+                }
+                bar_arrive(BAR_FULL + buf);
+                buf = buf + 1 == NB ? 0 : buf + 1;
+            }
+            return;
+        }
+#endif
+        // this thread's own two blocks / this warp's staging jobs
+        u32 pk[2], jm[2];
+        const int16_t *q0[2], *q1[2];    // lane pointers into run 0 / run 1 (lone blocks: the lane's own block)
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++) {
+            // pass 0: job wq.  Pass 1: the jobs after the first four, handed out so that a warp whose pass-0 job is a (cheap)
+            // chroma job gets one first -- without sub-sampling warps 0,1 transform luma and 2,3 take Cb, then Cr; in 4:2:2 the
+            // lone halo job goes to a chroma warp.  (4:2:0 / 4:4:0: all four pass-0 jobs are luma, order is irrelevant.)
+            const int jw = ps == 0 ? wq : ((wq + ((MODE == MODE_NONE || MODE == MODE_H) ? 2 : 0)) & 3);
+            setup_job(ps * ZF_PRODUCERS + jw * 32, pk[ps], q0[ps], q1[ps], jm[ps]);
+        }
         // loop-carried state
         const int16_t *qa0 = q0[0], *qb0 = q1[0], *qa1 = q0[1], *qb1 = q1[1];
         const u32 pk0 = pk[0], pk1 = pk[1], jm0 = jm[0], jm1 = jm[1];
@@ -1442,6 +1649,14 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         // one staging slot per thread: the copy of the next pass is issued as soon as the row pass has drained the slot
         // and lands while the column pass runs
         const bool work0 = __any_sync(0xffffffffu, (pk0 & 0x10000u) != 0), work1 = __any_sync(0xffffffffu, (pk1 & 0x10000u) != 0);   // any block in the warp
+        // the pass-1 job of this warp holds nothing but halo blocks (4:2:0: entries 192-203 of the list) ...
+        constexpr bool HALO_JOBS = ZF_HALO_COL && MODE == MODE_HV && !FT::DENSE && ((FT::NY + 2 * FT::NC) % 32) == 0;
+        const int jw1 = (wq + ((MODE == MODE_NONE || MODE == MODE_H) ? 2 : 0)) & 3;
+        bool halo1 = HALO_JOBS && (ZF_PRODUCERS + jw1 * 32 >= FT::NY + 2 * FT::NC);
+        // ... and may be reduced to the one column per block the consumers' packed path reads: not when a unit of the tile goes
+        // through the per-sample path (it reads halo samples anywhere), nor when the raw row tail (Q4g) starts left of the tile
+        // (decided in front of the first pass 1, see below)
+        const bool tail_in_halo = cb0 + ncb == mcu_x && W - 36 - cb0 * 8 < 0;
         issue(0, qa0, qb0, jm0);
         qa0 += st0; qb0 += st0;
         int buf = 0;
@@ -1460,7 +1675,17 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     issue(ps, ps ? qa0 : qa1, ps ? qb0 : qb1, ps ? (it + 1 < n_it ? jm0 : 0u) : jm1);
                     if (ps) { qa0 += st0; qb0 += st0; } else { qa1 += st1; qb1 += st1; }
                 };
-                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled<FT::IDCT_UNROLL>(active, active ? slx : zslot, scr, sQ[pkk >> 18], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, refill);
+                if (HALO_JOBS && ps && it == 0) {
+                    // the consumers have counted their per-sample units long before the producers' first pass 1 (they arrived at
+                    // this barrier when their queue was complete): nobody waits here, it only orders the read of the count
+                    asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_QUEUE + 2), "n"(ZF_THREADS) : "memory");
+                    halo1 = halo1 && sSlowN == 0 && !tail_in_halo;
+#ifdef ZF_HALO_FORCE_OFF
+                    halo1 = halo1 && spc < 0;      // (experiment: the code is there but never taken)
+#endif
+                }
+                const int halo = (HALO_JOBS && ps && halo1) ? ((pkk & 0x100000u) ? 2 : 1) : 0;
+                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled<FT::IDCT_UNROLL, HALO_JOBS>(active, active ? slx : zslot, scr, sQ[(pkk >> 18) & 3u], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, halo, refill);
                 else refill();
             }
             bar_arrive(BAR_FULL + buf);
@@ -1475,6 +1700,13 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const bool ycc = im.out_kind == OUT_YCC;
     u32 esel = (ZF_CONV_HI && !ycc) ? 0x7351u : 0x6240u, ekk = 0xC000C000u ^ ((u32)spc >> 30);   // (spc < 2^30: a constant ptxas cannot see)
     asm volatile("" : "+r"(esel), "+r"(ekk));   // (opaque: kept in registers instead of being rematerialised in front of every use)
+    u32 ekr = 0xE980E980u ^ ((u32)spc >> 30), emask = 0xFFFCFFFCu ^ ((u32)spc >> 30);
+#if ZF_KR
+    asm volatile("" : "+r"(ekr));
+#endif
+#if ZF_VSCALE == 2
+    asm volatile("" : "+r"(emask));
+#endif
     int xs = X0 + 16 * xu;                                // first sample of the unit in the padded row
     // Where the unit's 48 bytes go (worker.rs:201-246): samples < n_norm ("normal" 16-sample chunks) sit at
     // byte 3*s, except bytes the tail chunk overwrites; the tail chunk (samples Wp-16..Wp-1) sits at T; the rest is never written
@@ -1527,6 +1759,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
         }
     bar_sync_consumers(BAR_QUEUE);   // the queue is complete (consumer warps only)
     const int nslow = sSlowN;
+    if (ZF_HALO_COL && MODE == MODE_HV && !FT::DENSE && ((FT::NY + 2 * FT::NC) % 32) == 0) bar_arrive(BAR_QUEUE + 2);   // ... and the producers may read its length
 
     // bytes of a row nobody writes: [P, stride) minus the tail chunk [T, T+48) (Q5: 16 zero bytes; Q6: the w "alpha"
     // bytes) = [z0, stride); every tile zeroes its share, with the widest stores the alignment allows
@@ -1597,10 +1830,16 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                     const u32 B[4] = {lanes01(b.x), lanes23(b.x), lanes01(b.y), lanes23(b.y)};
                     const u32 Ah = aL | (aR << 16), Bh = bL | (bR << 16);
                     u32 N[4], F[4];
+                    u32 Nh, Fh;
+#if ZF_VSCALE
+#pragma unroll
+                    for (int k = 0; k < 4; k++) T2pair_s(A[k], B[k], N[k], F[k], emask);
+                    T2pair_s(Ah, Bh, Nh, Fh, emask);
+#else
 #pragma unroll
                     for (int k = 0; k < 4; k++) T2pair(A[k], B[k], N[k], F[k]);
-                    u32 Nh, Fh;
                     T2pair(Ah, Bh, Nh, Fh);
+#endif
                     // AVX2 form: lane 0 of a vector takes 3*(in+in'+2)>>2 of its OWN first element as "previous" value,
                     // lane 15 the same expression of the next vector's first element as "next" value (Q4e)
                     u32 pv = (3u * ((sel0 ? (a.x & 0xffu) + (b.x & 0xffu) : aR + bR) + 2u)) >> 2;
@@ -1619,11 +1858,19 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                             pv = (3u * (y0 + y1 + 2u)) >> 2;
                         }
                     }
+#if ZF_VSCALE
+                    pv = pv * 4u + (ZF_VSCALE == 2 ? 2u : 0u);            // (<= 4 * 384 + 2: one lane)
+#endif
                     const u32 keep = sel0 ? 0xffff0000u : 0x0000ffffu, ins = sel0 ? pv : pv << 16;
                     Nh = (Nh & keep) | ins;
                     Fh = (Fh & keep) | ins;
+#if ZF_VSCALE
+                    hfilter16_s(Nh, N, E0[c], O0[c]);
+                    hfilter16_s(Fh, F, E1[c], O1[c]);
+#else
                     hfilter16(Nh, N, E0[c], O0[c]);
                     hfilter16(Fh, F, E1[c], O1[c]);
+#endif
                     if (firstvec && cc0 == 0) E1[c][0] = prmt(E1[c][0], O1[c][0], 0x3254u);   // far rows: out[0] = out[1] (avx2.rs:330)
                 } else {
                     // last 32 outputs of the double-row: out[O+2k] = T(in[c], in[c-1]), out[O+2k+1] = T(in[c], in[c+1]),
@@ -1652,7 +1899,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 if (y_base + yl < im.height) {
                     u32 yw[4];
                     load16(planes + yl * TWY + xl, FT::H == 2 || y16, yw);
-                    emit16(out + (size_t)(y_base + yl) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec, esel, ekk);
+                    emit16(out + (size_t)(y_base + yl) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec, esel, ekk, ekr);
                 }
                 if (RPU == 2) {
 #pragma unroll
@@ -1665,12 +1912,12 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             if (y_base + yl0 < im.height) {
                 u32 yw[4];
                 load16(planes + yl0 * TWY + xl, FT::H == 2 || y16, yw);
-                emit16(out + (size_t)(y_base + yl0) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec, esel, ekk);
+                emit16(out + (size_t)(y_base + yl0) * stride + dst_off, yw, E0[0], O0[0], E0[1], O0[1], ycc, nw, vec, esel, ekk, ekr);
             }
             if (RPU == 2 && y_base + yl1 < im.height) {
                 u32 yw[4];
                 load16(planes + yl1 * TWY + xl, FT::H == 2 || y16, yw);
-                emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec, esel, ekk);
+                emit16(out + (size_t)(y_base + yl1) * stride + dst_off, yw, E1[0], O1[0], E1[1], O1[1], ycc, nw, vec, esel, ekk, ekr);
             }
 #endif
         }
@@ -1864,7 +2111,7 @@ gray_fast_kernel(const DevImage *__restrict__ images, const int spc)
             auto refill = [&]() {
                 if (it + 1 < n_it) { issue(q0, row_exists(it + 1)); q0 += step; }
             };
-            if (work && row_exists(it)) idct_rolled<ZF_UNROLL_GRAY>(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, refill);
+            if (work && row_exists(it)) idct_rolled<ZF_UNROLL_GRAY, false>(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, 0, refill);
             else refill();
             bar_arrive(BAR_FULL + (it & 1));
         }
