@@ -25,6 +25,9 @@
 #ifndef ZF_T2PAIR
 #define ZF_T2PAIR 1
 #endif
+#ifndef ZF_LO6
+#define ZF_LO6 1        // 1: a 6-input column pass for jobs whose rows 6-7 are zero in every block of the warp
+#endif
 #if ZF_HINTS
 #define ZF_LIKELY(x) __builtin_expect(!!(x), 1)
 #define ZF_UNLIKELY(x) __builtin_expect(!!(x), 0)
@@ -164,18 +167,17 @@ __device__ __forceinline__ void idct8_lo4(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u3
 template <int SH>
 __device__ __forceinline__ void idct8_lo6(u32 &s0, u32 &s1, u32 &s2, u32 &s3, u32 &s4, u32 &s5, u32 &s6, u32 &s7, const u32 bias)
 {
-    const u32 t2 = s2 * 2217u;                 // p1 + s6 * -7567 with s6 = 0
-    const u32 t3 = s2 * (2217u + 3135u);       // p1 + s2 * 3135
-    const u32 t0 = ((s0 + s4) << 12) + bias, t1 = ((s0 - s4) << 12) + bias;
-    const u32 x0 = t0 + t3, x3 = t0 - t3, x1 = t1 + t2, x2 = t1 - t2;
-    const u32 b = s5, c = s3, d = s1;          // a = s7 = 0
-    const u32 p4 = b + d, q2 = b + c;          // p3 = a + c = c, p1 = a + d = d
-    const u32 p5 = (c + p4) * 4816u;
-    const u32 r1 = p5 + d * (u32)(-3685);
-    const u32 r2 = p5 + q2 * (u32)(-10497);
-    const u32 m3 = c * (u32)(-8034);
-    const u32 m4 = p4 * (u32)(-1597);
-    const u32 dd = d * 6149u + r1 + m4, cc = c * 12586u + r2 + m3, bb = b * 8410u + r2 + m4, aa = r1 + m3;
+    // 35 operations
+    const u32 v = (s0 << 12) + bias;
+    const u32 t0 = madk<4096>(s4, v), t1 = madk<-4096>(s4, v);
+    const u32 x0 = madk<2217 + 3135>(s2, t0), x3 = madk<-(2217 + 3135)>(s2, t0), x1 = madk<2217>(s2, t1), x2 = madk<-2217>(s2, t1);
+    const u32 p4 = s5 + s1, q2 = s5 + s3;          // a = s7 = 0: p3 = c, q1 = d
+    const u32 p5 = (s3 + p4) * 4816u;
+    const u32 r1 = madk<-3685>(s1, p5), r2 = madk<-10497>(q2, p5);
+    const u32 aa = madk<-8034>(s3, r1);
+    const u32 cc = madk<12586 - 8034>(s3, r2);
+    const u32 bb = madk<8410>(s5, madk<-1597>(p4, r2));
+    const u32 dd = madk<6149>(s1, madk<-1597>(p4, r1));
     s0 = (u32)((int)(x0 + dd) >> SH);
     s1 = (u32)((int)(x1 + cc) >> SH);
     s2 = (u32)((int)(x2 + bb) >> SH);
@@ -432,7 +434,7 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
 // cache for more); 4 = unrolled (everything that depends on the row pair becomes static: +7 % on 4:2:2, +10 % luma-only)
 // halo: 0 = an ordinary job; warp-uniform non-zero = a job of halo blocks reduced to one column each (1: this lane's block
 // needs its first column, 2: its last column)
-template <int UNROLL, bool HALO, typename AfterRows>
+template <int UNROLL, bool HALO, bool LO6, typename AfterRows>
 __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, const u32 sc, const u32 *__restrict__ qtw, uint8_t *__restrict__ dst, const int dst_stride,
                                             const int halo, AfterRows after_rows)
 {
@@ -507,7 +509,7 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
     const u32 dc0 = carry;
     const bool rows45 = (nz & 4u) != 0, rows67 = (nz & 8u) != 0;
     const bool rows47 = rows45 || rows67;
-    if (rows47 && !(rows45 && rows67)) {       // the 8-input column pass reads rows 4-7: zero the pair that was skipped
+    if (rows47 && !(rows45 && rows67) && !(LO6 && rows45)) {       // the 8-input column pass reads rows 4-7: zero the pair that was skipped
         const u32 o = sc + (u32)(rows45 ? 12 : 8) * CH;
 #pragma unroll
         for (int k = 0; k < 4; k++) sts128(o + (u32)k * CH, 0u, 0u, 0u, 0u);
@@ -528,8 +530,13 @@ __device__ __forceinline__ void idct_rolled(const bool active, const u32 sl, con
         // (a halo job: column group 0 only, and a last column's four bytes go to block columns 4-7)
         const int g1 = halo_job ? 1 : 2;
         uint8_t *const d0 = (HALO && halo == 2) ? dst + 4 : dst;
+        if (LO6 && !rows67) {                 // rows 6-7 are zero in every block of the warp (five luma jobs in six of a quality-90 photo)
 #pragma unroll 1
-        for (int g = 0; g < g1; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, d0 + 4 * g, dst_stride);
+            for (int g = 0; g < g1; g++) col_pass<6>(active, dconly, dcword, sc + (u32)g * CH, d0 + 4 * g, dst_stride);
+        } else {
+#pragma unroll 1
+            for (int g = 0; g < g1; g++) col_pass<8>(active, dconly, dcword, sc + (u32)g * CH, d0 + 4 * g, dst_stride);
+        }
     }
 }
 
@@ -821,7 +828,7 @@ __device__ __forceinline__ void convert_pair(u32 y, u32 cb, u32 cr, u32 &r, u32 
 #define ZF_CONV_HI 2
 #endif
 #ifndef ZF_KR
-#define ZF_KR 1         // 1: the red channel's bias rides on a second lane constant (one 32-bit add fewer per lane pair, one register more)
+#define ZF_KR 2         // 1: the red channel's bias rides on a second lane constant (one 32-bit add fewer per lane pair, one register more)
 #endif
 __device__ __forceinline__ void convert_pair_hi(u32 y, u32 cb, u32 cr, u32 &r, u32 &g, u32 &b, const u32 k, const u32 kr)
 {
@@ -829,7 +836,15 @@ __device__ __forceinline__ void convert_pair_hi(u32 y, u32 cb, u32 cr, u32 &r, u
 #if ZF_CONV_HI == 2
     // every channel is biased so that ONE lane constant (-16384, kept in a register by the caller) brings it back: the biases
     // ride on immediates of 32-bit adds (all lanes stay inside [0, 65535], so the lanes never carry into each other)
-#if ZF_KR
+#if ZF_KR == 2
+    // red and green share y32g = 32y + 20767 (one LEA); red's lane constant takes the difference back (kr = -5760 - 20767, the
+    // lane-wise add wraps mod 2^16 and the true result lies in [-5760, 15315])
+    const u32 y32g = y * 32u + 0x511F511Fu;
+    r = minrelu2(vadd2(cr * 45u + y32g, kr), 0x1FFF1FFFu) * 8u;
+    g = minrelu2(vadd2(y32g - cb * 11u - cr * 23u, k), 0x1FFF1FFFu) * 8u;
+    b = minrelu2(vadd2(minu2(cb * 113u + y * 64u + 0x07800780u, 0x7FFF7FFFu), k), 0x3FFF3FFFu) * 4u;
+    return;
+#elif ZF_KR
     r = minrelu2(vadd2(cr * 45u + y32, kr), 0x1FFF1FFFu) * 8u;                                     // kr = -5760 on both lanes: 45cr + 32y never leaves [0, 21075]
 #else
     r = minrelu2(vadd2(cr * 45u + y32 + 0x29802980u, k), 0x1FFF1FFFu) * 8u;                        // +10624 = 16384 - 5760
@@ -1226,6 +1241,9 @@ template <int MODE> struct FastTraits {
     static constexpr int CS = TWC + 24;               // chroma smem row: left halo | tile | right halo | special
     static constexpr int NSLOT = MODE == MODE_H ? 2 : (MODE == MODE_HV ? 3 : 0);  // halo block columns per chroma plane
     // row-pair loop of the IDCT: unrolled where the instruction cache has room for it (measured per mode)
+    // a 6-input column pass for jobs whose rows 6-7 are zero in every block of the warp: pays where the row-pair loop is rolled or
+    // the strip is short (4:2:0 +1.1 %, 4:2:2 +0.6 %); with the unrolled loops of 4:4:4 / luma-only its code costs more than it saves
+    static constexpr bool LO6 = ZF_LO6 && (MODE == MODE_HV || MODE == MODE_H);
     static constexpr int IDCT_UNROLL = MODE == MODE_HV ? ZF_UNROLL_HV : (MODE == MODE_V ? ZF_UNROLL_V : (MODE == MODE_H ? ZF_UNROLL_H : ZF_UNROLL_NONE));
     static constexpr int NY = YBR * YB, NC = CBR * CB, PER = NC + NSLOT * CBR;
     static constexpr int YBYTES = ROWS * TWY, CBYTES = CROWS * CS, BUF = YBYTES + 2 * CBYTES;  // one buffer of sample planes
@@ -1620,7 +1638,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                         halo_ok = halo_ok && sSlowN == 0 && !tail_in_halo;
                     }
                     const int halo = (HALO_JOBS && ps && hasH && halo_ok) ? ((pkk & 0x100000u) ? 2 : 1) : 0;
-                    if (work) idct_rolled<FT::IDCT_UNROLL, HALO_JOBS>(active, active ? slx : zslot, scr, sQ[(pkk >> 18) & 3u], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, halo, refill);
+                    if (work) idct_rolled<FT::IDCT_UNROLL, HALO_JOBS, FT::LO6>(active, active ? slx : zslot, scr, sQ[(pkk >> 18) & 3u], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, halo, refill);
                     else refill();
                 }
                 bar_arrive(BAR_FULL + buf);
@@ -1685,7 +1703,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
 #endif
                 }
                 const int halo = (HALO_JOBS && ps && halo1) ? ((pkk & 0x100000u) ? 2 : 1) : 0;
-                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled<FT::IDCT_UNROLL, HALO_JOBS>(active, active ? slx : zslot, scr, sQ[(pkk >> 18) & 3u], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, halo, refill);
+                if (ps ? (work1 && !ZF_EXPERIMENT_SKIPC) : work0) idct_rolled<FT::IDCT_UNROLL, HALO_JOBS, FT::LO6>(active, active ? slx : zslot, scr, sQ[(pkk >> 18) & 3u], planes + (pkk & 0xffffu), (pkk & 0x20000u) ? CS : TWY, halo, refill);
                 else refill();
             }
             bar_arrive(BAR_FULL + buf);
@@ -1700,7 +1718,7 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
     const bool ycc = im.out_kind == OUT_YCC;
     u32 esel = (ZF_CONV_HI && !ycc) ? 0x7351u : 0x6240u, ekk = 0xC000C000u ^ ((u32)spc >> 30);   // (spc < 2^30: a constant ptxas cannot see)
     asm volatile("" : "+r"(esel), "+r"(ekk));   // (opaque: kept in registers instead of being rematerialised in front of every use)
-    u32 ekr = 0xE980E980u ^ ((u32)spc >> 30), emask = 0xFFFCFFFCu ^ ((u32)spc >> 30);
+    u32 ekr = (ZF_KR == 2 ? 0x98619861u : 0xE980E980u) ^ ((u32)spc >> 30), emask = 0xFFFCFFFCu ^ ((u32)spc >> 30);
 #if ZF_KR
     asm volatile("" : "+r"(ekr));
 #endif
@@ -2111,7 +2129,7 @@ gray_fast_kernel(const DevImage *__restrict__ images, const int spc)
             auto refill = [&]() {
                 if (it + 1 < n_it) { issue(q0, row_exists(it + 1)); q0 += step; }
             };
-            if (work && row_exists(it)) idct_rolled<ZF_UNROLL_GRAY, false>(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, 0, refill);
+            if (work && row_exists(it)) idct_rolled<ZF_UNROLL_GRAY, false, false>(active, active ? slx : zslot, scr, sQ, planes + dsto, ZG_TW, 0, refill);
             else refill();
             bar_arrive(BAR_FULL + (it & 1));
         }
