@@ -48,10 +48,10 @@
 #define ZF_EMIT_LOOP 0
 #endif
 #ifndef ZF_ROTATE_HV
-#define ZF_ROTATE_HV 0       // 4:2:0: the pass-1 producer jobs (Cb, Cr, halo) rotate over the four producer warps with the strip
+#define ZF_ROTATE_HV 0       // 4:2:0: the pass-1 producer jobs (Cb, Cr, halo) rotate over the four producer warps with the strip (measured: 589 against 608 GP/s with the static assignment -- kept for the record, off)
 #endif
 #ifndef ZF_DEFER_EMPTY
-#define ZF_DEFER_EMPTY 1     // (rotated form) wait for the plane buffer between the row pass and the column pass
+#define ZF_DEFER_EMPTY 1     // (rotated form) wait for the plane buffer between the row pass and the column pass (measured: no difference)
 #endif
 
 // The per-sample generic path (slow_pixel) used to be kept out of line.  With that call inside a consumer warp,
@@ -413,7 +413,7 @@ __device__ __forceinline__ void col_pass(const bool active, const bool dconly, c
 // a separate single-column column pass was measured too: 345 SASS lines more, and the 4:2:0 kernel LOST 5.5 % (instruction cache).
 // Only taken when no unit of the tile goes through the per-sample path and the raw row tail (Q4g) stays inside the tile.
 #ifndef ZF_HALO_COL
-#define ZF_HALO_COL 0
+#define ZF_HALO_COL 0      // (measured twice: 590 against 598 and 594 against 608 GP/s -- the extra hot code costs more than the instructions it saves; off)
 #endif
 #ifndef ZF_UNROLL_HV
 #define ZF_UNROLL_HV 1
@@ -828,7 +828,7 @@ __device__ __forceinline__ void convert_pair(u32 y, u32 cb, u32 cr, u32 &r, u32 
 #define ZF_CONV_HI 2
 #endif
 #ifndef ZF_KR
-#define ZF_KR 2         // 1: the red channel's bias rides on a second lane constant (one 32-bit add fewer per lane pair, one register more)
+#define ZF_KR 2         // 1: the red channel's bias rides on a second lane constant (one 32-bit add fewer per lane pair, one register more); 2: red and green also share the biased luma term
 #endif
 __device__ __forceinline__ void convert_pair_hi(u32 y, u32 cb, u32 cr, u32 &r, u32 &g, u32 &b, const u32 k, const u32 kr)
 {
