@@ -47,6 +47,9 @@
 #ifndef ZF_EMIT_LOOP
 #define ZF_EMIT_LOOP 0
 #endif
+#ifndef ZF_EARLY_NEXT
+#define ZF_EARLY_NEXT 1      // producers without a pass-1 job prefetch their next strip from pass 0 (see the producer loop)
+#endif
 #ifndef ZF_ROTATE_HV
 #define ZF_ROTATE_HV 0       // 4:2:0: the pass-1 producer jobs (Cb, Cr, halo) rotate over the four producer warps with the strip (measured: 589 against 608 GP/s with the static assignment -- kept for the record, off)
 #endif
@@ -1217,7 +1220,7 @@ reconstruct_kernel(const DevImage *__restrict__ images)
 // Same arithmetic as above, organised as a producer / consumer pipeline inside one CTA of 256 threads that owns one
 // tile column of `spc` consecutive strips:
 //   * warps 0-3 (producers) run the IDCT: two passes of one 8x8 block per thread fill the strip's sample planes in
-//     shared memory (double-buffered), the next strip's coefficients are prefetched into L2 on the way;
+//     shared memory (double-buffered);
 //   * warps 4-7 (consumers) turn the planes into pixels: every thread produces two UNITS per strip, a unit being 16
 //     luma columns (one conv16 chunk of the reference, color_convert/avx.rs:67-107) of one output row (NONE, H) or
 //     of the two rows that share their chroma inputs (V, HV).
@@ -1392,9 +1395,6 @@ __device__ __forceinline__ void load16(const uint8_t *p, const bool a16, u32 w[4
 #endif
 #ifndef ZF_ROLEMAP
 #define ZF_ROLEMAP 0    // 0: warps 0-3 produce, 4-7 consume (both roles on every SM sub-partition); 1: sub-partitions 0,1 produce, 2,3 consume
-#endif
-#ifndef ZF_PREFETCH
-#define ZF_PREFETCH 1   // next strip's coefficients: 0 nothing, 1 prefetch.global.L2, 2 prefetch.global.L1
 #endif
 enum { BAR_FULL = 1, BAR_EMPTY = 1 + ZF_NBUF, BAR_QUEUE = 1 + 2 * ZF_NBUF };  // + buffer index
 
@@ -1682,6 +1682,11 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             ST *planes = sPlanes + buf * FT::BUF;
 #pragma unroll 1
             for (int ps = 0; ps < 2; ps++) {
+                // A warp without a pass-1 job (4:2:2: every warp -- the strip-tile's list is exactly one pass) copies its NEXT
+                // strip's job as soon as the row pass of pass 0 has drained the slot, and skips pass 1: issued from pass 1 the copy
+                // had no lead at all -- the warp waited for it at the top of the next strip (10 % of all stall samples of the
+                // 1080p 4:2:2 config sat on that wait).
+                if (ZF_EARLY_NEXT && !HALO_JOBS && ps == 1 && !work1) break;
                 const u32 pkk = ps ? pk1 : pk0;
                 const bool active = (pkk & 0x10000u) != 0;
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1690,8 +1695,9 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
                 // the copy issued from this pass: the warp's pass-1 job of this strip, or its pass-0 job of the next strip
                 // (one call site: the copy code exists once in the loop)
                 auto refill = [&]() {
-                    issue(ps, ps ? qa0 : qa1, ps ? qb0 : qb1, ps ? (it + 1 < n_it ? jm0 : 0u) : jm1);
-                    if (ps) { qa0 += st0; qb0 += st0; } else { qa1 += st1; qb1 += st1; }
+                    const bool nxt = ps || (ZF_EARLY_NEXT && !HALO_JOBS && !work1);           // the next strip's pass-0 job
+                    issue(ps, nxt ? qa0 : qa1, nxt ? qb0 : qb1, nxt ? (it + 1 < n_it ? jm0 : 0u) : jm1);
+                    if (nxt) { qa0 += st0; qb0 += st0; } else { qa1 += st1; qb1 += st1; }
                 };
                 if (HALO_JOBS && ps && it == 0) {
                     // the consumers have counted their per-sample units long before the producers' first pass 1 (they arrived at
