@@ -51,7 +51,7 @@
 #define ZF_EARLY_NEXT 1      // producers without a pass-1 job prefetch their next strip from pass 0 (see the producer loop)
 #endif
 #ifndef ZF_ROTATE_HV
-#define ZF_ROTATE_HV 0       // 4:2:0: the pass-1 producer jobs (Cb, Cr, halo) rotate over the four producer warps with the strip (measured: 589 against 608 GP/s with the static assignment -- kept for the record, off)
+#define ZF_ROTATE_HV 0       // 4:2:0: the pass-1 producer jobs (Cb, Cr, halo) rotate over the four producer warps with the strip (measured: 589 against 608 GP/s with the static assignment, 626 against 643 once both forms copied early -- kept for the record, off)
 #endif
 #ifndef ZF_DEFER_EMPTY
 #define ZF_DEFER_EMPTY 1     // (rotated form) wait for the plane buffer between the row pass and the column pass (measured: no difference)
@@ -1609,8 +1609,11 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
             for (int it = 0; it < n_it; it++) {
                 ST *planes = sPlanes + buf * FT::BUF;
                 const bool hasC = (it & 1) == half, hasH = !hasC && ((it >> 1) & 1) == pair;
+                // a strip without a pass-1 job: the next strip's luma job is copied from pass 0 and pass 1 is skipped (ZF_EARLY_NEXT)
+                const bool early = ZF_EARLY_NEXT && !HALO_JOBS && !(hasC || hasH);
 #pragma unroll 1
                 for (int ps = 0; ps < 2; ps++) {
+                    if (ps == 1 && early) break;
                     const u32 pkk = ps ? (hasC ? pkC : pkH) : pkL;
                     const bool work = ps ? (hasC ? workC : (hasH && workH)) : workL;
                     const bool active = (pkk & 0x10000u) != 0;
@@ -1624,10 +1627,11 @@ reconstruct_fast_kernel(const DevImage *__restrict__ images, const int spc)
 #if ZF_DEFER_EMPTY
                         if (ps == 0 && it >= NB) bar_sync(BAR_EMPTY + buf);   // the consumers are done with this buffer
 #endif
-                        const int16_t *g0 = ps ? aL : (hasC ? aC : aH), *g1 = ps ? bL : (hasC ? bC : aH);
-                        const u32 m = ps ? (it + 1 < n_it ? jmL : 0u) : (hasC ? jmC : (hasH ? jmH : 0u));
+                        const bool nxt = ps || early;
+                        const int16_t *g0 = nxt ? aL : (hasC ? aC : aH), *g1 = nxt ? bL : (hasC ? bC : aH);
+                        const u32 m = nxt ? (it + 1 < n_it ? jmL : 0u) : (hasC ? jmC : (hasH ? jmH : 0u));
                         issue(ps, g0, g1, m);
-                        if (ps) { aL += stepY; bL += stepY; }
+                        if (nxt) { aL += stepY; bL += stepY; }
                         else if (hasC) { aC += 2u * stepC; bC += 2u * stepC; }
                         else if (hasH) aH += 4u * stepC;
                     };
