@@ -241,6 +241,31 @@ def test_sparse_and_dense_blocks_mix():
         assert np.array_equal(got, want), mode
 
 
+@pytest.mark.parametrize("mode", list(MODES))
+def test_warp_uniform_sparsity_classes_at_the_limits(mode):
+    """Every short form of the rolled IDCT taken by WHOLE warps (the class is the same in every block of a plane), with
+    coefficients over the full i16 range and quantisers up to 255: the regrouped butterflies (idct8 / idct8_lo4 / idct8_lo6 --
+    multiply-adds re-associated in Z/2^32, `ZF_IDCT_MAD`) and the 4- / 6- / 8-input column passes must wrap exactly like the
+    oracle's literal form.  Classes = (rows kept, columns kept)."""
+    from zune_jpeg_b200 import gpu
+    rng = np.random.default_rng(4242)
+    hs, vs = MODES[mode]
+    w, h = 528, 96
+    qts = [rng.integers(1, 256, size=64).astype(np.int32) for _ in range(3)]
+    qts[1][:] = 255
+    for (rk, ck) in [(8, 8), (6, 8), (6, 4), (4, 8), (4, 4), (8, 4), (7, 8), (5, 6), (2, 2), (1, 8), (8, 1), (6, 2)]:
+        for out_cs in (0, 2):
+            planes = util.random_planes(rng, w, h, 3, hs, vs, extreme=True, dc_only_frac=0.05)
+            for p in planes:
+                blk = p.reshape(-1, 8, 8)
+                blk[:, rk:, :] = 0
+                blk[:, :, ck:] = 0
+            img = util.make_image(w, h, planes, qts, hs, vs, out_cs, 0)
+            want = oracle.reconstruct(img)
+            got = gpu.reconstruct([img])[0]
+            assert np.array_equal(got, want), (mode, rk, ck, out_cs, int((got != want).sum()))
+
+
 def test_gray_fast_kernel_corners():
     """Luma-only output through gray_fast_kernel: odd block-row counts, ragged widths, colour inputs of every sub-sampling,
     unaligned output pointers."""
